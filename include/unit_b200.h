@@ -1,0 +1,200 @@
+/*
+ * unit_b200 -- C ABI of the B200-native UniT RoI stage (libunit_b200.so, sm_100a).
+ *
+ * Every entry point replaces one interface the reference (ubc-vision/UniT) reaches through Detectron2 /
+ * torchvision on its RoI path; the reference file:line that calls it is cited per function (paths relative to
+ * the reference root; [D2] = Detectron2, [TV] = torchvision, both un-vendored dependencies).
+ *
+ * Conventions
+ *   - plain pointers + sizes; no torch types.  All pointers are DEVICE pointers unless the name ends in _host.
+ *   - the caller owns every buffer including workspaces; kernels never allocate, free or retain pointers.
+ *   - all work is enqueued on `stream` (a cudaStream_t); no host synchronisation, no default-stream use.
+ *   - return 0 on success, a negative UNIT_E* code on failure; unit_last_error() gives the thread-local text.
+ *   - boxes are xyxy fp32; class / index outputs are int64 where the reference's are (PyTorch LongTensor).
+ *   - variable-length outputs are written into caller-sized maximum buffers with a device-side count.
+ */
+#ifndef UNIT_B200_H_
+#define UNIT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* unit_stream_t; /* cudaStream_t */
+
+enum {
+  UNIT_OK = 0,
+  UNIT_EINVAL = -1,    /* bad shape / dtype / alignment / null pointer */
+  UNIT_ECUDA = -2,     /* launch or runtime failure; text has cudaGetErrorString */
+  UNIT_EWORKSPACE = -3 /* workspace too small */
+};
+
+enum { UNIT_F32 = 0, UNIT_BF16 = 1 };
+
+int unit_version(void);
+const char* unit_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
+unsigned long long unit_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * ROIAlign forward / backward.
+ * Replaces [D2] ROIPooler -> ROIAlign(aligned=True) == [TV] torch.ops.torchvision.roi_align /
+ * _roi_align_backward; reference call sites modeling/roi_heads/roi_heads.py:356,364,499,511,598,610,708,715,
+ * 729,829,843,911 (`self.box_pooler(features, [x.proposal_boxes ...])`).
+ *   feat      [N,C,H,W]  NCHW, dtype f32 or bf16          rois [R,5] fp32 (batch_idx, x1, y1, x2, y2)
+ *   out       [R,C,PH,PW] same dtype as feat
+ *   rois_sorted != 0: rois are grouped by ascending batch index (what ROIPooler produces); enables the
+ *   slab-resident kernel.  workspace: unit_roi_align_workspace_bytes(N) bytes.
+ * Backward writes grad_feat [N,C,H,W] completely (no pre-zeroing needed by the caller).
+ */
+size_t unit_roi_align_workspace_bytes(int N);
+int unit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, int C, int H, int W, int R, int PH,
+                       int PW, float spatial_scale, int sampling_ratio, int aligned, int dtype, int rois_sorted,
+                       void* workspace, size_t workspace_bytes, unit_stream_t stream);
+int unit_roi_align_bwd(const void* grad_out, const float* rois, void* grad_feat, int N, int C, int H, int W, int R,
+                       int PH, int PW, float spatial_scale, int sampling_ratio, int aligned, int dtype,
+                       int rois_sorted, void* workspace, size_t workspace_bytes, unit_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * pairwise IoU.  Replaces [D2] structures.pairwise_iou (weak_detector_fast_rcnn.py:327-329,411 and inside
+ * [D2] ROIHeads.label_and_sample_proposals reached at roi_heads.py:459,563,794,925).
+ *   iou[g*P + p] = inter > 0 ? inter / ((area1 + area2) - inter) : 0, each op rounded to fp32 (no FMA).
+ */
+int unit_pairwise_iou(const float* boxes1, const float* boxes2, float* iou, int G, int P, unit_stream_t stream);
+
+/* Matcher on a given [G,P] quality matrix.  Replaces modeling/matcher.py:54-119 (UniT, 3 outputs) and [D2]
+ * Matcher (2 outputs: pass matched_vals = NULL).  thresholds_host: the T user thresholds (ascending, without the
+ * +-inf sentinels); labels_host: T+1 labels in {-1,0,1}.  G == 0 -> matches 0, labels labels_host[0], vals 0.
+ * workspace: G floats (only read when allow_low_quality_matches). */
+int unit_matcher(const float* iou, int G, int P, const float* thresholds_host, const int* labels_host, int T,
+                 int allow_low_quality_matches, int64_t* matches, int8_t* match_labels, float* matched_vals,
+                 void* workspace, size_t workspace_bytes, unit_stream_t stream);
+
+/* Fused pairwise_iou + Matcher for every image of a batch in one launch (no [G,P] matrix in HBM).
+ * gt_offsets / prop_offsets: int32 [n_img+1] prefix sums (device).  Outputs are indexed by global proposal row;
+ * matches are image-local GT indices. */
+int unit_iou_match(const float* gt_boxes, const int* gt_offsets, const float* prop_boxes, const int* prop_offsets,
+                   int n_img, int P_total, const float* thresholds_host, const int* labels_host, int T,
+                   int64_t* matches, int8_t* match_labels, float* matched_vals, unit_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * fg/bg labelling + sampling.  Replaces [D2] ROIHeads._sample_proposals + sampling.subsample_labels
+ * (roi_heads.py:415 and via label_and_sample_proposals) and weak_detector_fast_rcnn.py:308-318.
+ * Step 1 (unit_label_proposals): prop_classes = gt_classes[matches]; label 0 -> num_classes; label -1 -> -1;
+ *   no GT -> num_classes.  pos_idx / neg_idx: per image, ascending image-local indices of foreground / background
+ *   proposals, stored from prop_offsets[i]; counts[2*i], counts[2*i+1] = #pos, #neg.
+ * Step 2 (unit_sample_gather): the host draws randperm(#pos), randperm(#neg) (the reference's two draws per image)
+ *   and passes them concatenated; *_sel_offsets are int32 [n_img+1] prefix sums of the TAKEN counts
+ *   (num_pos = min(#pos, int(batch*frac)), num_neg = min(#neg, batch-num_pos)), perm_*_offsets the prefix sums of
+ *   the FULL permutation lengths.  Output row j of image i: j < num_pos ? pos[perm_pos[j]] : neg[perm_neg[j-num_pos]].
+ */
+int unit_label_proposals(const int64_t* matches, const int8_t* match_labels, const int64_t* gt_classes,
+                         const int* gt_offsets, const int* prop_offsets, int n_img, int P_total, int num_classes,
+                         int64_t* prop_classes, int64_t* pos_idx, int64_t* neg_idx, int* counts,
+                         unit_stream_t stream);
+int unit_sample_gather(const int64_t* pos_idx, const int64_t* neg_idx, const int64_t* perm_pos,
+                       const int* perm_pos_offsets, const int64_t* perm_neg, const int* perm_neg_offsets,
+                       const int* pos_sel_offsets, const int* neg_sel_offsets, const int* prop_offsets,
+                       const int* gt_offsets, int n_img, int S_total, const float* prop_boxes,
+                       const int64_t* prop_classes, const int64_t* matches, const float* gt_boxes,
+                       int64_t* sampled_idx, float* out_boxes, int64_t* out_classes, int64_t* out_matched,
+                       float* out_gt_boxes, unit_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * softmax + Box2BoxTransform.apply_deltas.  Replaces [D2] FastRCNNOutputLayers.predict_probs / predict_boxes
+ * (fast_rcnn.py:456,459; meta_arch/rcnn.py:525) and weak_detector_fast_rcnn.py:270-287.
+ *   probs [R,K1] (nullable), boxes [R,4*KB] (nullable).  weights = (wx,wy,ww,wh); dw,dh clamped to scale_clamp. */
+int unit_softmax_decode(const float* scores, const float* deltas, const float* proposals, float* probs, float* boxes,
+                        int R, int K1, int KB, float wx, float wy, float ww, float wh, float scale_clamp,
+                        unit_stream_t stream);
+/* Box2BoxTransform.get_deltas (fast_rcnn.py:69-71 via FastRCNNOutputs.box_reg_loss). */
+int unit_box_get_deltas(const float* src, const float* tgt, float* deltas, int R, float wx, float wy, float ww,
+                        float wh, unit_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * fast_rcnn_inference for a batch of images in two launches.  Replaces [D2] fast_rcnn_inference(_single_image)
+ * (fast_rcnn.py:461-468, weak_detector_fast_rcnn.py:299-306, meta_arch/rcnn.py:526): drop non-finite rows, drop
+ * the background column, clip to the image, score > thresh, row-major (roi, class) candidates, class-wise batched
+ * NMS, top-k.
+ *   boxes [R,4*KB], probs [R,K+1], roi_offsets int32 [n_img+1], image_hw fp32 [n_img,2] (h,w), all device.
+ * unit_detect_filter writes per-image candidate segments starting at roi_offsets[i]*K:
+ *   cand_boxes [R*K,4], cand_scores [R*K], cand_roi/cand_cls int32 [R*K], cand_counts int32 [n_img].
+ * unit_detect_nms consumes them and writes det_* [n_img, topk(...)] + det_counts [n_img].
+ *   nms_mode: 0 = class-wise on the raw boxes (torchvision _batched_nms_vanilla), 1 = coordinate trick
+ *   (boxes + cls*(max+1), torchvision _batched_nms_coordinate_trick), 2 = follow torchvision's CUDA rule
+ *   (coordinate trick iff 4*Nc <= 100000), 3 = torchvision's CPU rule (4*Nc <= 4000).
+ */
+int unit_detect_filter(const float* boxes, const float* probs, const int* roi_offsets, const float* image_hw,
+                       int n_img, int R, int K, int KB, float score_thresh, float* cand_boxes, float* cand_scores,
+                       int* cand_roi, int* cand_cls, int* cand_counts, unit_stream_t stream);
+size_t unit_nms_workspace_bytes(int n_seg, int total_candidates);
+int unit_detect_nms(const float* cand_boxes, const float* cand_scores, const int* cand_roi, const int* cand_cls,
+                    const int* cand_counts, const int* roi_offsets, int n_img, int R, int K, float nms_thresh,
+                    int nms_mode,
+                    int topk, float* det_boxes, float* det_scores, int64_t* det_classes, int64_t* det_roi,
+                    int* det_counts, void* workspace, size_t workspace_bytes, unit_stream_t stream);
+/* torchvision.ops.batched_nms / nms drop-in ([D2] layers.batched_nms, imported at fast_rcnn.py:9).
+ *   idxs int64 [N] (NULL -> plain nms).  keep int64 [N] sorted by descending score (ties: lower index first),
+ *   keep_count int32 [1].  max_keep < 0 -> all. */
+int unit_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int N, float iou_thresh,
+                     int nms_mode, int max_keep, int64_t* keep, int* keep_count, void* workspace,
+                     size_t workspace_bytes, unit_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Lingual similarity.  Replaces fast_rcnn.py:376-382 `get_similarity` (+ the softmax of roi_heads.py:272).
+ *   emb [V,D]; indexer int64 [K]; base int64 [B]; novel int64 [Nn]; raw / soft: [Nn,B] (either nullable). */
+int unit_lingual_similarity(const float* emb, const int64_t* indexer, const int64_t* base, const int64_t* novel,
+                            int D, int B, int Nn, float* raw, float* soft, unit_stream_t stream);
+
+/* Visual similarity + combination + base->novel transfer, fused per RoI.
+ * Replaces roi_heads.py:245-336 `get_similarity_matrices` (Sum combination; class-level terms are pre-reduced by
+ * the host into static_*) and fast_rcnn.py:403-426 / 503-528 (transfer, + weak scores, + fine-tune terms).
+ *   vis_logits [R,K+1]   mean OICR logits of the box-head features (NULL when no head uses 'visual')
+ *   static_cls/bbox/seg [Nn,B]  sum of the class-level terms already multiplied by their 1/len(terms) weight
+ *   wv_*            weight of the visual term for that head (0 = absent);  norm_* = divide by clamp(sum,1e-9)
+ *   class_kind int32 [K]: -1 neither, 0..B-1 -> base slot + 0, 1000000+n -> novel slot n
+ *   delta_scores [R,K+1], proposal_deltas [R,4K] in; weak_scores [R,K+1], ft_scores, ft_deltas nullable
+ *   out_scores [R,K+1], out_bbox [R,4K]; out_s_cls / out_s_bbox / out_s_seg [R,Nn,B] nullable
+ *   do_transfer == 0 -> scores/bbox pass through (training of the Base predictor, fast_rcnn.py:401)
+ *   novel_neg_inf != 0 -> novel logits := -inf (fast_rcnn.py:427-428)
+ */
+typedef struct {
+  int R, K, B, Nn;
+  float vis_threshold;
+  float wv_cls, wv_bbox, wv_seg;
+  int norm_cls, norm_bbox, norm_seg;
+  int do_transfer, novel_neg_inf;
+} unit_transfer_params;
+int unit_similarity_transfer(const unit_transfer_params* p, const float* vis_logits, const float* static_cls,
+                             const float* static_bbox, const float* static_seg, const int* base, const int* novel,
+                             const int* class_kind, const float* delta_scores, const float* proposal_deltas,
+                             const float* weak_scores, const float* ft_scores, const float* ft_deltas,
+                             float* out_scores, float* out_bbox, float* out_s_cls, float* out_s_bbox,
+                             float* out_s_seg, unit_stream_t stream);
+/* Gradient of the transfer w.r.t. delta_scores / proposal_deltas for fixed similarity (S is built under frozen
+ * weights in every shipped fine-tune YAML).  detach_transfer != 0 reproduces the .detach() of fast_rcnn.py:566,575. */
+int unit_similarity_transfer_bwd(const unit_transfer_params* p, const float* s_cls, const float* s_bbox,
+                                 const int* base, const int* novel, const int* class_kind, const float* g_scores,
+                                 const float* g_bbox, int detach_transfer, float* g_delta_scores,
+                                 float* g_proposal_deltas, unit_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Mask transfer + class select + sigmoid.  Replaces mask_head.py:16-37 / 72-94 and [D2] mask_rcnn_inference.
+ *   logits [D,K,M,M]; s_seg [D,Nn,B] (s_is_2d: [Nn,B]); x_delta [D,K,M,M] nullable; pred_classes int64 [D].
+ *   out_logits [D,K,M,M] nullable (full transferred tensor); out_probs [D,1,M,M] nullable. */
+int unit_mask_transfer(const float* logits, const float* s_seg, int s_is_2d, const int* base, const int* novel,
+                       const int* class_kind, const float* x_delta, const int64_t* pred_classes, float* out_logits,
+                       float* out_probs, int D, int K, int B, int Nn, int MM, unit_stream_t stream);
+/* paste_masks_in_image.  Replaces [D2] layers.mask_ops.paste_masks_in_image via detector_postprocess
+ * (meta_arch/rcnn.py:423).  masks [D,M,M] probabilities, boxes [D,4]; out uint8/bool [D,img_h,img_w] = bilinear
+ * sample (align_corners=False, zero padding) >= threshold. */
+int unit_mask_paste(const float* masks, const float* boxes, int D, int M, int img_h, int img_w, float threshold,
+                    uint8_t* out, unit_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIT_B200_H_ */

@@ -1,0 +1,459 @@
+// Base -> novel knowledge transfer.
+//
+//   lingual similarity     fast_rcnn.py:376-382 (+ softmax of roi_heads.py:272)
+//   visual similarity      roi_heads.py:246-257
+//   combination            roi_heads.py:266-322 ('Sum' mode; class-level terms arrive pre-reduced in static_*)
+//   transfer               fast_rcnn.py:403-426 / 503-528, weak scores :360-368, fine-tune terms :527-528
+//   mask transfer          mask_head.py:16-37 / 72-94 + [D2] mask_rcnn_inference
+//   mask paste             [D2] paste_masks_in_image (meta_arch/rcnn.py:423 via detector_postprocess)
+//
+// One 128-thread CTA per RoI fuses what the reference does with ~30 ATen launches (softmax, index_select,
+// renormalise, threshold, broadcast add, renormalise, 2 x bmm with 5x15 / 20x60 matrices, index_copy, adds).
+// The dense predictor GEMMs feeding this epilogue are K=2048 contractions and run on tensor cores (gemm.cu /
+// cuBLAS); this file is the memory-bound part and never leaves fp32.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace unit {
+namespace transfer {
+
+constexpr int NOVEL_TAG = 1000000;
+
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------- lingual similarity
+__global__ void lingual_kernel(const float* __restrict__ emb, const int64_t* __restrict__ indexer,
+                               const int64_t* __restrict__ base, const int64_t* __restrict__ novel, int D, int B,
+                               float* __restrict__ raw, float* __restrict__ soft) {
+  extern __shared__ float s_raw[];  // [B]
+  const int n = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const float* en = emb + indexer[novel[n]] * D;
+  for (int b = warp; b < B; b += nwarp) {
+    const float* eb = emb + indexer[base[b]] * D;
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) acc = fmaf(en[d], eb[d], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s_raw[b] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float m = -INFINITY;
+    for (int b = lane; b < B; b += 32) m = fmaxf(m, s_raw[b]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int b = lane; b < B; b += 32) sum += expf(s_raw[b] - m);
+    sum = warp_sum(sum);
+    for (int b = lane; b < B; b += 32) {
+      if (raw) raw[n * B + b] = s_raw[b];
+      if (soft) soft[n * B + b] = expf(s_raw[b] - m) / sum;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- fused transfer
+constexpr int TT = 128;
+
+struct TransferArgs {
+  unit_transfer_params p;
+  const float* vis_logits;
+  const float* stat[3];  // cls, bbox, seg
+  const int* base;
+  const int* novel;
+  const int* class_kind;
+  const float* delta_scores;
+  const float* proposal_deltas;
+  const float* weak_scores;
+  const float* ft_scores;
+  const float* ft_deltas;
+  float* out_scores;
+  float* out_bbox;
+  float* out_s[3];
+};
+
+__global__ void __launch_bounds__(TT) similarity_transfer_kernel(const TransferArgs a) {
+  extern __shared__ float sm[];
+  const int K = a.p.K, B = a.p.B, Nn = a.p.Nn, K1 = K + 1;
+  float* s_v = sm;              // [B]   visual similarity
+  float* s_delta = s_v + B;     // [K1]
+  float* s_pd = s_delta + K1;   // [4K]
+  float* s_tc = s_pd + 4 * K;   // [Nn]  transferred class logits
+  float* s_tb = s_tc + Nn;      // [4Nn] transferred box deltas
+  __shared__ float s_red[2];
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = TT / 32;
+
+  for (int k = tid; k < K1; k += TT) s_delta[k] = a.delta_scores[(long long)r * K1 + k];
+  for (int k = tid; k < 4 * K; k += TT) s_pd[k] = a.proposal_deltas[(long long)r * 4 * K + k];
+
+  const bool need_v = a.p.do_transfer && (a.p.wv_cls != 0.f || a.p.wv_bbox != 0.f || a.p.wv_seg != 0.f);
+  if (need_v) {
+    // softmax over all K+1 OICR logits, base columns, renormalise, threshold (roi_heads.py:255-257)
+    const float* vl = a.vis_logits + (long long)r * K1;
+    if (warp == 0) {
+      float m = -INFINITY;
+      for (int k = lane; k < K1; k += 32) m = fmaxf(m, vl[k]);
+      m = warp_max(m);
+      float sum = 0.f;
+      for (int k = lane; k < K1; k += 32) sum += expf(vl[k] - m);
+      sum = warp_sum(sum);
+      float bs = 0.f;
+      for (int b = lane; b < B; b += 32) {
+        const float pv = expf(vl[a.base[b]] - m) / sum;
+        s_v[b] = pv;
+        bs += pv;
+      }
+      bs = warp_sum(bs);
+      const float den = fmaxf(bs, 1e-9f);
+      for (int b = lane; b < B; b += 32) {
+        float v = s_v[b] / den;
+        if (v < a.p.vis_threshold) v = 0.f;
+        s_v[b] = v;
+      }
+    }
+  } else {
+    for (int b = tid; b < B; b += TT) s_v[b] = 0.f;
+  }
+  __syncthreads();
+  (void)s_red;
+
+  if (a.p.do_transfer) {
+    const float wv[3] = {a.p.wv_cls, a.p.wv_bbox, a.p.wv_seg};
+    const int nrm[3] = {a.p.norm_cls, a.p.norm_bbox, a.p.norm_seg};
+    for (int h = 0; h < 3; ++h) {
+      if (h == 2 && !a.out_s[2]) continue;  // the seg similarity is only materialised for the mask head
+      for (int n = warp; n < Nn; n += nwarp) {
+        const float* st = a.stat[h] ? a.stat[h] + n * B : nullptr;
+        float sum = 0.f;
+        for (int b = lane; b < B; b += 32) sum += (st ? st[b] : 0.f) + wv[h] * s_v[b];
+        sum = warp_sum(sum);
+        const float inv_den = nrm[h] ? 1.f / fmaxf(sum, 1e-9f) : 1.f;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        for (int b = lane; b < B; b += 32) {
+          float s = (st ? st[b] : 0.f) + wv[h] * s_v[b];
+          s = nrm[h] ? s / fmaxf(sum, 1e-9f) : s;
+          if (a.out_s[h]) a.out_s[h][((long long)r * Nn + n) * B + b] = s;
+          const int kb = a.base[b];
+          if (h == 0) {
+            acc0 = fmaf(s, s_delta[kb], acc0);
+          } else if (h == 1) {
+            acc0 = fmaf(s, s_pd[4 * kb + 0], acc0);
+            acc1 = fmaf(s, s_pd[4 * kb + 1], acc1);
+            acc2 = fmaf(s, s_pd[4 * kb + 2], acc2);
+            acc3 = fmaf(s, s_pd[4 * kb + 3], acc3);
+          }
+        }
+        (void)inv_den;
+        if (h == 0) {
+          acc0 = warp_sum(acc0);
+          if (lane == 0) s_tc[n] = acc0;
+        } else if (h == 1) {
+          acc0 = warp_sum(acc0);
+          acc1 = warp_sum(acc1);
+          acc2 = warp_sum(acc2);
+          acc3 = warp_sum(acc3);
+          if (lane == 0) {
+            s_tb[4 * n + 0] = acc0;
+            s_tb[4 * n + 1] = acc1;
+            s_tb[4 * n + 2] = acc2;
+            s_tb[4 * n + 3] = acc3;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  for (int k = tid; k < K1; k += TT) {
+    float v = s_delta[k];
+    const int kind = k < K ? a.class_kind[k] : -1;
+    if (a.p.do_transfer && kind >= NOVEL_TAG) v = v + s_tc[kind - NOVEL_TAG];
+    if (a.weak_scores) v = v + a.weak_scores[(long long)r * K1 + k];
+    if (a.ft_scores) v = v + a.ft_scores[(long long)r * K1 + k];
+    if (a.p.novel_neg_inf && kind >= NOVEL_TAG) v = -INFINITY;
+    a.out_scores[(long long)r * K1 + k] = v;
+  }
+  for (int i = tid; i < 4 * K; i += TT) {
+    const int k = i >> 2, j = i & 3;
+    float v = s_pd[i];
+    if (a.p.do_transfer) {
+      const int kind = a.class_kind[k];
+      if (kind >= NOVEL_TAG) v = s_tb[4 * (kind - NOVEL_TAG) + j];
+      else if (kind < 0) v = 0.f;
+    }
+    if (a.ft_deltas) v = v + a.ft_deltas[(long long)r * 4 * K + i];
+    a.out_bbox[(long long)r * 4 * K + i] = v;
+  }
+}
+
+struct TransferBwdArgs {
+  int R, K, B, Nn;
+  const float* s_cls;
+  const float* s_bbox;
+  const int* base;
+  const int* novel;
+  const int* class_kind;
+  const float* g_scores;
+  const float* g_bbox;
+  int detach;
+  float* g_delta;
+  float* g_pd;
+};
+
+__global__ void __launch_bounds__(TT) similarity_transfer_bwd_kernel(const TransferBwdArgs a) {
+  const int K = a.K, B = a.B, Nn = a.Nn, K1 = K + 1;
+  const int r = blockIdx.x, tid = threadIdx.x;
+  // scores: identity everywhere; base columns additionally collect sum_n S_cls[n,b] * g[novel n]
+  for (int k = tid; k < K1; k += TT) {
+    float g = a.g_scores[(long long)r * K1 + k];
+    const int kind = k < K ? a.class_kind[k] : -1;
+    if (!a.detach && kind >= 0 && kind < NOVEL_TAG) {
+      const int b = kind;
+      for (int n = 0; n < Nn; ++n)
+        g = fmaf(a.s_cls[((long long)r * Nn + n) * B + b], a.g_scores[(long long)r * K1 + a.novel[n]], g);
+    }
+    a.g_delta[(long long)r * K1 + k] = g;
+  }
+  for (int i = tid; i < 4 * K; i += TT) {
+    const int k = i >> 2, j = i & 3;
+    const int kind = a.class_kind[k];
+    float g = 0.f;
+    if (kind >= 0 && kind < NOVEL_TAG) {
+      g = a.g_bbox[(long long)r * 4 * K + i];
+      if (!a.detach)
+        for (int n = 0; n < Nn; ++n)
+          g = fmaf(a.s_bbox[((long long)r * Nn + n) * B + kind], a.g_bbox[(long long)r * 4 * K + 4 * a.novel[n] + j], g);
+    }
+    a.g_pd[(long long)r * 4 * K + i] = g;
+  }
+}
+
+// ---------------------------------------------------------------------------------------- mask transfer
+__global__ void mask_transfer_kernel(const float* __restrict__ logits, const float* __restrict__ s_seg, int s_is_2d,
+                                     const int* __restrict__ base, const int* __restrict__ class_kind,
+                                     const float* __restrict__ x_delta, const int64_t* __restrict__ pred_classes,
+                                     float* __restrict__ out_logits, float* __restrict__ out_probs, int K, int B,
+                                     int Nn, int MM) {
+  const int d = blockIdx.x;
+  const float* lg = logits + (long long)d * K * MM;
+  const float* S = s_seg ? s_seg + (s_is_2d ? 0 : (long long)d * Nn * B) : nullptr;
+  if (out_logits) {
+    for (int i = threadIdx.x; i < K * MM; i += blockDim.x) {
+      const int k = i / MM, m = i - k * MM;
+      float v = lg[i];
+      if (S) {
+        const int kind = class_kind[k];
+        if (kind >= NOVEL_TAG) {
+          const float* sr = S + (kind - NOVEL_TAG) * B;
+          float acc = 0.f;
+          for (int b = 0; b < B; ++b) acc = fmaf(sr[b], lg[base[b] * MM + m], acc);
+          v = acc;
+        } else if (kind < 0) {
+          v = 0.f;
+        }
+      }
+      if (x_delta) v = v + x_delta[(long long)d * K * MM + i];
+      out_logits[(long long)d * K * MM + i] = v;
+    }
+  }
+  if (out_probs) {
+    const int k = (int)pred_classes[d];
+    const int kind = class_kind[k];
+    for (int m = threadIdx.x; m < MM; m += blockDim.x) {
+      float v = lg[k * MM + m];
+      if (S) {
+        if (kind >= NOVEL_TAG) {
+          const float* sr = S + (kind - NOVEL_TAG) * B;
+          float acc = 0.f;
+          for (int b = 0; b < B; ++b) acc = fmaf(sr[b], lg[base[b] * MM + m], acc);
+          v = acc;
+        } else if (kind < 0) {
+          v = 0.f;
+        }
+      }
+      if (x_delta) v = v + x_delta[((long long)d * K + k) * MM + m];
+      out_probs[(long long)d * MM + m] = 1.f / (1.f + expf(-v));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- mask paste
+// out[d,y,x] = bilinear(mask_d, grid(x,y)) >= thr with F.grid_sample(align_corners=False, zeros) semantics.
+// Thread = 16 consecutive output bytes (one 16-byte store); runs entirely outside the box window are zero-filled
+// without sampling (about 95 % of an 800x1333 canvas).
+__device__ __forceinline__ float paste_sample(const float* __restrict__ mk, int M, float gx, float gy) {
+  const float half = (float)M * 0.5f;
+  const float ix = __fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), half), 0.5f);
+  const float iy = __fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), half), 0.5f);
+  const float xw = floorf(ix), yn = floorf(iy);
+  const float w = __fsub_rn(ix, xw), e = __fsub_rn(1.f, w);
+  const float n = __fsub_rn(iy, yn), s = __fsub_rn(1.f, n);
+  const int x0 = (int)xw, y0 = (int)yn;
+  auto at = [&](int y, int x) -> float { return (x >= 0 && x < M && y >= 0 && y < M) ? mk[y * M + x] : 0.f; };
+  const float nw = __fmul_rn(at(y0, x0), __fmul_rn(s, e));
+  const float ne = __fmul_rn(at(y0, x0 + 1), __fmul_rn(s, w));
+  const float sw = __fmul_rn(at(y0 + 1, x0), __fmul_rn(n, e));
+  const float se = __fmul_rn(at(y0 + 1, x0 + 1), __fmul_rn(n, w));
+  return __fadd_rn(__fadd_rn(__fadd_rn(nw, ne), sw), se);
+}
+
+__global__ void mask_paste_kernel(const float* __restrict__ masks, const float4* __restrict__ boxes, int D, int M,
+                                  int H, int W, float thr, uint8_t* __restrict__ out) {
+  const long long total = (long long)D * H * W;
+  const long long start = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (start >= total) return;
+  const long long hw = (long long)H * W;
+  int d = (int)(start / hw);
+  long long rem = start - (long long)d * hw;
+  int y = (int)(rem / W), x = (int)(rem - (long long)y * W);
+  unsigned char v[16];
+  float4 bx = __ldg(boxes + d);
+  for (int i = 0; i < 16; ++i) {
+    unsigned char o = 0;
+    if (start + i < total) {
+      const float bw = __fsub_rn(bx.z, bx.x), bh = __fsub_rn(bx.w, bx.y);
+      // quick reject: sample index must lie in (-1, M) on both axes
+      const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+      const float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(px, bx.x), bw), 2.f), 1.f);
+      const float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(py, bx.y), bh), 2.f), 1.f);
+      const float lim = 1.f + 2.f / (float)M;
+      if (fabsf(gx) < lim && fabsf(gy) < lim) {
+        const float val = paste_sample(masks + (long long)d * M * M, M, gx, gy);
+        o = val >= thr ? 1 : 0;
+      } else if (!(gx == gx) || !(gy == gy)) {
+        const float val = paste_sample(masks + (long long)d * M * M, M, gx, gy);
+        o = val >= thr ? 1 : 0;
+      } else {
+        o = 0.f >= thr ? 1 : 0;
+      }
+      if (++x == W) {
+        x = 0;
+        if (++y == H) {
+          y = 0;
+          ++d;
+          if (d < D) bx = __ldg(boxes + d);
+        }
+      }
+    }
+    v[i] = o;
+  }
+  if (start + 16 <= total && ((((uintptr_t)out) + start) & 15) == 0) {
+    uint4 q;
+    memcpy(&q, v, 16);
+    *reinterpret_cast<uint4*>(out + start) = q;
+  } else {
+    for (int i = 0; i < 16 && start + i < total; ++i) out[start + i] = v[i];
+  }
+}
+
+}  // namespace transfer
+}  // namespace unit
+
+using namespace unit;
+using namespace unit::transfer;
+
+extern "C" {
+
+int unit_lingual_similarity(const float* emb, const int64_t* indexer, const int64_t* base, const int64_t* novel,
+                            int D, int B, int Nn, float* raw, float* soft, unit_stream_t stream) {
+  UNIT_REQUIRE(D > 0 && B > 0 && Nn >= 0, "lingual_similarity: bad shape");
+  if (Nn == 0) return UNIT_OK;
+  UNIT_REQUIRE(emb && indexer && base && novel && (raw || soft), "lingual_similarity: null pointer");
+  lingual_kernel<<<Nn, 128, B * sizeof(float), (cudaStream_t)stream>>>(emb, indexer, base, novel, D, B, raw, soft);
+  UNIT_CHECK_LAUNCH("lingual_kernel");
+  return UNIT_OK;
+}
+
+int unit_similarity_transfer(const unit_transfer_params* p, const float* vis_logits, const float* static_cls,
+                             const float* static_bbox, const float* static_seg, const int* base, const int* novel,
+                             const int* class_kind, const float* delta_scores, const float* proposal_deltas,
+                             const float* weak_scores, const float* ft_scores, const float* ft_deltas,
+                             float* out_scores, float* out_bbox, float* out_s_cls, float* out_s_bbox,
+                             float* out_s_seg, unit_stream_t stream) {
+  UNIT_REQUIRE(p, "similarity_transfer: null params");
+  UNIT_REQUIRE(p->R >= 0 && p->K > 0 && p->B >= 0 && p->Nn >= 0, "similarity_transfer: bad shape");
+  if (p->R == 0) return UNIT_OK;
+  UNIT_REQUIRE(delta_scores && proposal_deltas && out_scores && out_bbox && class_kind,
+               "similarity_transfer: null pointer");
+  const bool need_v = p->do_transfer && (p->wv_cls != 0.f || p->wv_bbox != 0.f || p->wv_seg != 0.f);
+  UNIT_REQUIRE(!need_v || vis_logits, "similarity_transfer: a head uses the visual term but vis_logits is NULL");
+  UNIT_REQUIRE(!p->do_transfer || (base && novel) || (p->B == 0 && p->Nn == 0),
+               "similarity_transfer: base/novel index arrays missing");
+  TransferArgs a;
+  a.p = *p;
+  a.vis_logits = vis_logits;
+  a.stat[0] = static_cls;
+  a.stat[1] = static_bbox;
+  a.stat[2] = static_seg;
+  a.base = base;
+  a.novel = novel;
+  a.class_kind = class_kind;
+  a.delta_scores = delta_scores;
+  a.proposal_deltas = proposal_deltas;
+  a.weak_scores = weak_scores;
+  a.ft_scores = ft_scores;
+  a.ft_deltas = ft_deltas;
+  a.out_scores = out_scores;
+  a.out_bbox = out_bbox;
+  a.out_s[0] = out_s_cls;
+  a.out_s[1] = out_s_bbox;
+  a.out_s[2] = out_s_seg;
+  const size_t smem = (size_t)(p->B + (p->K + 1) + 4 * p->K + 5 * p->Nn + 8) * sizeof(float);
+  similarity_transfer_kernel<<<p->R, TT, smem, (cudaStream_t)stream>>>(a);
+  UNIT_CHECK_LAUNCH("similarity_transfer_kernel");
+  return UNIT_OK;
+}
+
+int unit_similarity_transfer_bwd(const unit_transfer_params* p, const float* s_cls, const float* s_bbox,
+                                 const int* base, const int* novel, const int* class_kind, const float* g_scores,
+                                 const float* g_bbox, int detach_transfer, float* g_delta_scores,
+                                 float* g_proposal_deltas, unit_stream_t stream) {
+  UNIT_REQUIRE(p, "similarity_transfer_bwd: null params");
+  if (p->R == 0) return UNIT_OK;
+  UNIT_REQUIRE(g_scores && g_bbox && g_delta_scores && g_proposal_deltas && class_kind,
+               "similarity_transfer_bwd: null pointer");
+  UNIT_REQUIRE(detach_transfer || (s_cls && s_bbox && base && novel), "similarity_transfer_bwd: similarity missing");
+  TransferBwdArgs a = {p->R, p->K, p->B, p->Nn, s_cls, s_bbox, base, novel, class_kind,
+                       g_scores, g_bbox, detach_transfer, g_delta_scores, g_proposal_deltas};
+  similarity_transfer_bwd_kernel<<<p->R, TT, 0, (cudaStream_t)stream>>>(a);
+  UNIT_CHECK_LAUNCH("similarity_transfer_bwd_kernel");
+  return UNIT_OK;
+}
+
+int unit_mask_transfer(const float* logits, const float* s_seg, int s_is_2d, const int* base, const int* novel,
+                       const int* class_kind, const float* x_delta, const int64_t* pred_classes, float* out_logits,
+                       float* out_probs, int D, int K, int B, int Nn, int MM, unit_stream_t stream) {
+  (void)novel;
+  UNIT_REQUIRE(D >= 0 && K > 0 && MM > 0, "mask_transfer: bad shape");
+  if (D == 0) return UNIT_OK;
+  UNIT_REQUIRE(logits && class_kind && (out_logits || out_probs), "mask_transfer: null pointer");
+  UNIT_REQUIRE(!out_probs || pred_classes, "mask_transfer: out_probs needs pred_classes");
+  UNIT_REQUIRE(!s_seg || base, "mask_transfer: similarity given without base indices");
+  mask_transfer_kernel<<<D, 256, 0, (cudaStream_t)stream>>>(logits, s_seg, s_is_2d, base, class_kind, x_delta,
+                                                            pred_classes, out_logits, out_probs, K, B, Nn, MM);
+  UNIT_CHECK_LAUNCH("mask_transfer_kernel");
+  return UNIT_OK;
+}
+
+int unit_mask_paste(const float* masks, const float* boxes, int D, int M, int img_h, int img_w, float threshold,
+                    uint8_t* out, unit_stream_t stream) {
+  UNIT_REQUIRE(D >= 0 && M > 0 && img_h > 0 && img_w > 0, "mask_paste: bad shape");
+  if (D == 0) return UNIT_OK;
+  UNIT_REQUIRE(masks && boxes && out, "mask_paste: null pointer");
+  UNIT_REQUIRE((((uintptr_t)boxes) & 15) == 0, "mask_paste: boxes must be 16-byte aligned");
+  const long long total = (long long)D * img_h * img_w;
+  const long long threads = (total + 15) / 16;
+  mask_paste_kernel<<<cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(masks, (const float4*)boxes, D, M, img_h,
+                                                                         img_w, threshold, out);
+  UNIT_CHECK_LAUNCH("mask_paste_kernel");
+  return UNIT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,489 @@
+"""Tensor-level entry points of the RoI stage: every function enqueues hand-written sm_100a kernels from
+libunit_b200.so on the current CUDA stream through the C ABI (include/unit_b200.h).
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); there is no CPU path and no fallback:
+a CPU tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import TransferParams, check, lib
+
+_F32 = torch.float32
+NOVEL_TAG = 1000000
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("unit_b200 ops run on CUDA tensors only (there is no CPU path)")
+        dev = t.device
+    if dev is None:
+        raise RuntimeError("unit_b200 op called without tensors")
+    return dev
+
+
+def _c(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+_WS = {}
+
+
+def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _WS[key] = ws
+    return ws
+
+
+def _i32(values: Sequence[int], dev: torch.device) -> torch.Tensor:
+    return torch.tensor(list(values), dtype=torch.int32, device=dev)
+
+
+def offsets_from_counts(counts: Sequence[int], dev: torch.device) -> torch.Tensor:
+    off = [0]
+    for c in counts:
+        off.append(off[-1] + int(c))
+    return _i32(off, dev)
+
+
+# ------------------------------------------------------------------------------------------------- ROIAlign
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _lib.UNIT_F32
+    if t.dtype == torch.bfloat16:
+        return _lib.UNIT_BF16
+    raise RuntimeError(f"roi_align: unsupported dtype {t.dtype} (f32 and bf16 only)")
+
+
+def roi_align_forward(feat: torch.Tensor, rois: torch.Tensor, output_size: Tuple[int, int], spatial_scale: float,
+                      sampling_ratio: int, aligned: bool, rois_sorted: bool) -> torch.Tensor:
+    dev = _need_cuda(feat, rois)
+    feat = _c(feat)
+    rois = _c(rois, _F32)
+    N, C, H, W = feat.shape
+    R = rois.shape[0]
+    ph, pw = output_size
+    out = torch.empty((R, C, ph, pw), dtype=feat.dtype, device=dev)
+    if R == 0:
+        return out
+    ws_bytes = lib().unit_roi_align_workspace_bytes(N)
+    ws = _workspace(dev, ws_bytes)
+    check(lib().unit_roi_align_fwd(_ptr(feat), _ptr(rois), _ptr(out), N, C, H, W, R, ph, pw, float(spatial_scale),
+                                   int(sampling_ratio), int(bool(aligned)), _dtype_code(feat), int(bool(rois_sorted)),
+                                   _ptr(ws), ws.numel(), _stream()), "unit_roi_align_fwd")
+    return out
+
+
+def roi_align_backward(grad_out: torch.Tensor, rois: torch.Tensor, input_shape: Sequence[int], spatial_scale: float,
+                       sampling_ratio: int, aligned: bool, rois_sorted: bool) -> torch.Tensor:
+    dev = _need_cuda(grad_out, rois)
+    grad_out = _c(grad_out)
+    rois = _c(rois, _F32)
+    N, C, H, W = [int(v) for v in input_shape]
+    R, _, ph, pw = grad_out.shape
+    grad_in = torch.empty((N, C, H, W), dtype=grad_out.dtype, device=dev)
+    ws_bytes = lib().unit_roi_align_workspace_bytes(N)
+    ws = _workspace(dev, ws_bytes)
+    check(lib().unit_roi_align_bwd(_ptr(grad_out), _ptr(rois), _ptr(grad_in), N, C, H, W, R, ph, pw,
+                                   float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
+                                   _dtype_code(grad_out), int(bool(rois_sorted)), _ptr(ws), ws.numel(), _stream()),
+          "unit_roi_align_bwd")
+    return grad_in
+
+
+class _ROIAlignFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, rois, output_size, spatial_scale, sampling_ratio, aligned, rois_sorted):
+        ctx.save_for_backward(rois)
+        ctx.cfg = (tuple(feat.shape), spatial_scale, sampling_ratio, aligned, rois_sorted)
+        return roi_align_forward(feat, rois, output_size, spatial_scale, sampling_ratio, aligned, rois_sorted)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (rois,) = ctx.saved_tensors
+        shape, scale, sr, aligned, srt = ctx.cfg
+        return roi_align_backward(grad_out, rois, shape, scale, sr, aligned, srt), None, None, None, None, None, None
+
+
+def roi_align(feat: torch.Tensor, rois: torch.Tensor, output_size, spatial_scale: float = 1.0,
+              sampling_ratio: int = 0, aligned: bool = True, rois_sorted: bool = False) -> torch.Tensor:
+    """[TV] torchvision.ops.roi_align / [D2] ROIAlign drop-in (rois: [R,5] batch_idx,x1,y1,x2,y2)."""
+    if isinstance(output_size, int):
+        output_size = (output_size, output_size)
+    return _ROIAlignFn.apply(feat, rois, tuple(output_size), float(spatial_scale), int(sampling_ratio), bool(aligned),
+                             bool(rois_sorted))
+
+
+# ------------------------------------------------------------------------------------------------- IoU / matcher
+def pairwise_iou(boxes1: torch.Tensor, boxes2: torch.Tensor) -> torch.Tensor:
+    """[D2] pairwise_iou on raw [G,4] / [P,4] tensors -> [G,P]."""
+    dev = _need_cuda(boxes1, boxes2)
+    b1, b2 = _c(boxes1, _F32), _c(boxes2, _F32)
+    G, Pn = b1.shape[0], b2.shape[0]
+    out = torch.empty((G, Pn), dtype=_F32, device=dev)
+    if G and Pn:
+        check(lib().unit_pairwise_iou(_ptr(b1), _ptr(b2), _ptr(out), G, Pn, _stream()), "unit_pairwise_iou")
+    return out
+
+
+def _thr_arrays(thresholds: Sequence[float], labels: Sequence[int]):
+    T = len(thresholds)
+    thr = (ctypes.c_float * T)(*[float(t) for t in thresholds])
+    lab = (ctypes.c_int * (T + 1))(*[int(l) for l in labels])
+    return thr, lab, T
+
+
+def matcher(iou: torch.Tensor, thresholds: Sequence[float], labels: Sequence[int],
+            allow_low_quality_matches: bool = False, want_vals: bool = True):
+    """modeling/matcher.py Matcher.__call__ on a [G,P] quality matrix -> (matches i64, labels i8[, vals f32])."""
+    dev = _need_cuda(iou)
+    iou = _c(iou, _F32)
+    G, Pn = iou.shape
+    matches = torch.empty((Pn,), dtype=torch.int64, device=dev)
+    mlabels = torch.empty((Pn,), dtype=torch.int8, device=dev)
+    vals = torch.empty((Pn,), dtype=_F32, device=dev) if want_vals else None
+    thr, lab, T = _thr_arrays(thresholds, labels)
+    ws = _workspace(dev, max(G, 1) * 4)
+    check(lib().unit_matcher(_ptr(iou), G, Pn, thr, lab, T, int(bool(allow_low_quality_matches)), _ptr(matches),
+                             _ptr(mlabels), _ptr(vals), _ptr(ws), ws.numel(), _stream()), "unit_matcher")
+    return (matches, mlabels, vals) if want_vals else (matches, mlabels)
+
+
+def iou_match(gt_boxes: torch.Tensor, gt_offsets: torch.Tensor, prop_boxes: torch.Tensor, prop_offsets: torch.Tensor,
+              thresholds: Sequence[float], labels: Sequence[int], want_vals: bool = True):
+    """Fused pairwise_iou + Matcher for all images (offsets: int32 [n_img+1] on device)."""
+    dev = _need_cuda(prop_boxes, prop_offsets, gt_offsets)
+    gt_boxes, prop_boxes = _c(gt_boxes, _F32), _c(prop_boxes, _F32)
+    n_img = prop_offsets.numel() - 1
+    Pt = prop_boxes.shape[0]
+    matches = torch.empty((Pt,), dtype=torch.int64, device=dev)
+    mlabels = torch.empty((Pt,), dtype=torch.int8, device=dev)
+    vals = torch.empty((Pt,), dtype=_F32, device=dev) if want_vals else None
+    thr, lab, T = _thr_arrays(thresholds, labels)
+    check(lib().unit_iou_match(_ptr(gt_boxes), _ptr(gt_offsets), _ptr(prop_boxes), _ptr(prop_offsets), n_img, Pt, thr,
+                               lab, T, _ptr(matches), _ptr(mlabels), _ptr(vals), _stream()), "unit_iou_match")
+    return matches, mlabels, vals
+
+
+def label_proposals(matches, mlabels, gt_classes, gt_offsets, prop_offsets, num_classes: int):
+    """-> prop_classes i64 [P], pos_idx i64 [P], neg_idx i64 [P] (per-image compacted), counts i32 [n_img,2]."""
+    dev = _need_cuda(matches)
+    n_img = prop_offsets.numel() - 1
+    Pt = matches.numel()
+    prop_classes = torch.empty((Pt,), dtype=torch.int64, device=dev)
+    pos_idx = torch.empty((Pt,), dtype=torch.int64, device=dev)
+    neg_idx = torch.empty((Pt,), dtype=torch.int64, device=dev)
+    counts = torch.zeros((n_img, 2), dtype=torch.int32, device=dev)
+    gt_classes = _c(gt_classes, torch.int64)
+    check(lib().unit_label_proposals(_ptr(matches), _ptr(mlabels), _ptr(gt_classes), _ptr(gt_offsets),
+                                     _ptr(prop_offsets), n_img, Pt, int(num_classes), _ptr(prop_classes),
+                                     _ptr(pos_idx), _ptr(neg_idx), _ptr(counts), _stream()), "unit_label_proposals")
+    return prop_classes, pos_idx, neg_idx, counts
+
+
+def sample_gather(pos_idx, neg_idx, perm_pos, perm_pos_off, perm_neg, perm_neg_off, pos_sel_off, neg_sel_off,
+                  prop_offsets, gt_offsets, S_total: int, prop_boxes, prop_classes, matches, gt_boxes):
+    dev = _need_cuda(pos_idx)
+    n_img = prop_offsets.numel() - 1
+    sampled = torch.empty((S_total,), dtype=torch.int64, device=dev)
+    out_boxes = torch.empty((S_total, 4), dtype=_F32, device=dev)
+    out_classes = torch.empty((S_total,), dtype=torch.int64, device=dev)
+    out_matched = torch.empty((S_total,), dtype=torch.int64, device=dev)
+    out_gt = torch.empty((S_total, 4), dtype=_F32, device=dev)
+    check(lib().unit_sample_gather(_ptr(pos_idx), _ptr(neg_idx), _ptr(perm_pos), _ptr(perm_pos_off), _ptr(perm_neg),
+                                   _ptr(perm_neg_off), _ptr(pos_sel_off), _ptr(neg_sel_off), _ptr(prop_offsets),
+                                   _ptr(gt_offsets), n_img, S_total, _ptr(_c(prop_boxes, _F32)), _ptr(prop_classes),
+                                   _ptr(matches), _ptr(_c(gt_boxes, _F32)), _ptr(sampled), _ptr(out_boxes),
+                                   _ptr(out_classes), _ptr(out_matched), _ptr(out_gt), _stream()),
+          "unit_sample_gather")
+    return sampled, out_boxes, out_classes, out_matched, out_gt
+
+
+# ------------------------------------------------------------------------------------------------- decode / NMS
+SCALE_CLAMP = math.log(1000.0 / 16)
+
+
+def softmax_decode(scores: Optional[torch.Tensor], deltas: Optional[torch.Tensor], proposals: Optional[torch.Tensor],
+                   weights=(10.0, 10.0, 5.0, 5.0), scale_clamp: float = SCALE_CLAMP, want_probs=True, want_boxes=True):
+    dev = _need_cuda(scores, deltas)
+    R = (scores if scores is not None else deltas).shape[0]
+    probs = boxes = None
+    K1 = scores.shape[1] if scores is not None else 1
+    KB = deltas.shape[1] // 4 if deltas is not None else 0
+    if want_probs:
+        scores = _c(scores, _F32)
+        probs = torch.empty((R, K1), dtype=_F32, device=dev)
+    if want_boxes:
+        deltas = _c(deltas, _F32)
+        proposals = _c(proposals, _F32)
+        boxes = torch.empty((R, 4 * KB), dtype=_F32, device=dev)
+    if R:
+        check(lib().unit_softmax_decode(_ptr(scores) if want_probs else None, _ptr(deltas) if want_boxes else None,
+                                        _ptr(proposals) if want_boxes else None, _ptr(probs), _ptr(boxes), R, K1, KB,
+                                        float(weights[0]), float(weights[1]), float(weights[2]), float(weights[3]),
+                                        float(scale_clamp), _stream()), "unit_softmax_decode")
+    return probs, boxes
+
+
+def box_get_deltas(src: torch.Tensor, tgt: torch.Tensor, weights=(10.0, 10.0, 5.0, 5.0)) -> torch.Tensor:
+    dev = _need_cuda(src, tgt)
+    src, tgt = _c(src, _F32), _c(tgt, _F32)
+    R = src.shape[0]
+    out = torch.empty((R, 4), dtype=_F32, device=dev)
+    if R:
+        check(lib().unit_box_get_deltas(_ptr(src), _ptr(tgt), _ptr(out), R, float(weights[0]), float(weights[1]),
+                                        float(weights[2]), float(weights[3]), _stream()), "unit_box_get_deltas")
+    return out
+
+
+NMS_CLASSWISE, NMS_COORD_TRICK, NMS_TV_CUDA_RULE, NMS_TV_CPU_RULE = 0, 1, 2, 3
+
+
+def detect(boxes: torch.Tensor, probs: torch.Tensor, roi_offsets: torch.Tensor, image_hw: torch.Tensor,
+           score_thresh: float, nms_thresh: float, topk: int, nms_mode: int = NMS_TV_CUDA_RULE):
+    """fast_rcnn_inference for a batch: returns det_boxes [n,topk,4], det_scores [n,topk], det_classes i64,
+    det_roi i64 (index into the image's finite rows), det_counts i32 [n] -- all on device, no sync."""
+    dev = _need_cuda(boxes, probs)
+    boxes, probs = _c(boxes, _F32), _c(probs, _F32)
+    n_img = roi_offsets.numel() - 1
+    R, K1 = probs.shape
+    K = K1 - 1
+    KB = boxes.shape[1] // 4
+    cap = max(R * K, 1)
+    cand_boxes = torch.empty((cap, 4), dtype=_F32, device=dev)
+    cand_scores = torch.empty((cap,), dtype=_F32, device=dev)
+    cand_roi = torch.empty((cap,), dtype=torch.int32, device=dev)
+    cand_cls = torch.empty((cap,), dtype=torch.int32, device=dev)
+    cand_counts = torch.empty((max(n_img, 1),), dtype=torch.int32, device=dev)
+    check(lib().unit_detect_filter(_ptr(boxes), _ptr(probs), _ptr(roi_offsets), _ptr(image_hw), n_img, R, K, KB,
+                                   float(score_thresh), _ptr(cand_boxes), _ptr(cand_scores), _ptr(cand_roi),
+                                   _ptr(cand_cls), _ptr(cand_counts), _stream()), "unit_detect_filter")
+    topk = int(topk) if topk >= 0 else cap
+    det_boxes = torch.empty((n_img, topk, 4), dtype=_F32, device=dev)
+    det_scores = torch.empty((n_img, topk), dtype=_F32, device=dev)
+    det_classes = torch.empty((n_img, topk), dtype=torch.int64, device=dev)
+    det_roi = torch.empty((n_img, topk), dtype=torch.int64, device=dev)
+    det_counts = torch.empty((max(n_img, 1),), dtype=torch.int32, device=dev)
+    ws_bytes = lib().unit_nms_workspace_bytes(n_img, R * K)
+    ws = _workspace(dev, ws_bytes)
+    check(lib().unit_detect_nms(_ptr(cand_boxes), _ptr(cand_scores), _ptr(cand_roi), _ptr(cand_cls),
+                                _ptr(cand_counts), _ptr(roi_offsets), n_img, R, K, float(nms_thresh), int(nms_mode),
+                                topk, _ptr(det_boxes), _ptr(det_scores), _ptr(det_classes), _ptr(det_roi),
+                                _ptr(det_counts), _ptr(ws), ws.numel(), _stream()), "unit_detect_nms")
+    return det_boxes, det_scores, det_classes, det_roi, det_counts, (cand_boxes, cand_scores, cand_roi, cand_cls,
+                                                                      cand_counts)
+
+
+def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: Optional[torch.Tensor], iou_threshold: float,
+                nms_mode: int = NMS_TV_CUDA_RULE, max_keep: int = -1) -> torch.Tensor:
+    """[TV] torchvision.ops.batched_nms (idxs given) / nms (idxs None) drop-in: int64 indices, score-descending."""
+    dev = _need_cuda(boxes, scores)
+    boxes, scores = _c(boxes.float()), _c(scores, _F32)
+    N = boxes.shape[0]
+    if N == 0:
+        return torch.empty((0,), dtype=torch.int64, device=dev)
+    if idxs is not None:
+        idxs = _c(idxs, torch.int64)
+    keep = torch.empty((N,), dtype=torch.int64, device=dev)
+    count = torch.empty((1,), dtype=torch.int32, device=dev)
+    ws_bytes = lib().unit_nms_workspace_bytes(1, N)
+    ws = _workspace(dev, ws_bytes)
+    check(lib().unit_batched_nms(_ptr(boxes), _ptr(scores), _ptr(idxs), N, float(iou_threshold), int(nms_mode),
+                                 int(max_keep), _ptr(keep), _ptr(count), _ptr(ws), ws.numel(), _stream()),
+          "unit_batched_nms")
+    return keep[: int(count.item())]  # same host sync the reference's nms performs
+
+
+def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torch.Tensor:
+    return batched_nms(boxes, scores, None, iou_threshold)
+
+
+# ------------------------------------------------------------------------------------------------- transfer
+def lingual_similarity(emb: torch.Tensor, indexer: torch.Tensor, base: torch.Tensor, novel: torch.Tensor):
+    """fast_rcnn.py:376-382 -> (raw [Nn,B], softmax(raw, -1))."""
+    dev = _need_cuda(emb)
+    emb = _c(emb, _F32)
+    indexer, base, novel = _c(indexer, torch.int64), _c(base, torch.int64), _c(novel, torch.int64)
+    B, Nn = base.numel(), novel.numel()
+    raw = torch.empty((Nn, B), dtype=_F32, device=dev)
+    soft = torch.empty((Nn, B), dtype=_F32, device=dev)
+    check(lib().unit_lingual_similarity(_ptr(emb), _ptr(indexer), _ptr(base), _ptr(novel), emb.shape[1], B, Nn,
+                                        _ptr(raw), _ptr(soft), _stream()), "unit_lingual_similarity")
+    return raw, soft
+
+
+def make_class_kind(num_classes: int, base: Sequence[int], novel: Sequence[int], dev) -> torch.Tensor:
+    kind = [-1] * num_classes
+    for i, b in enumerate(base):
+        kind[int(b)] = i
+    for i, n in enumerate(novel):
+        kind[int(n)] = NOVEL_TAG + i
+    return _i32(kind, dev)
+
+
+class TransferSpec:
+    """Static (per model) part of the transfer: class index sets, class-level similarity terms, term weights."""
+
+    def __init__(self, num_classes: int, base: Sequence[int], novel: Sequence[int], dev,
+                 static: Optional[dict] = None, wv: Optional[dict] = None, norm: Optional[dict] = None,
+                 vis_threshold: float = 0.0):
+        self.K, self.B, self.Nn = int(num_classes), len(base), len(novel)
+        self.base_i32 = _i32(base, dev)
+        self.novel_i32 = _i32(novel, dev)
+        self.class_kind = make_class_kind(num_classes, base, novel, dev)
+        self.static = {k: (None if v is None else _c(v.to(dev), _F32)) for k, v in (static or {}).items()}
+        self.wv = dict(wv or {})
+        self.norm = dict(norm or {})
+        self.vis_threshold = float(vis_threshold)
+
+    def params(self, R: int, do_transfer: bool, novel_neg_inf: bool) -> TransferParams:
+        g = lambda d, k, default: d.get(k, default)
+        return TransferParams(R, self.K, self.B, self.Nn, self.vis_threshold,
+                              float(g(self.wv, "cls", 0.0)), float(g(self.wv, "bbox", 0.0)),
+                              float(g(self.wv, "seg", 0.0)),
+                              int(g(self.norm, "cls", 0)), int(g(self.norm, "bbox", 0)), int(g(self.norm, "seg", 0)),
+                              int(do_transfer), int(novel_neg_inf))
+
+
+def similarity_transfer_forward(spec: TransferSpec, vis_logits, delta_scores, proposal_deltas, weak_scores=None,
+                                ft_scores=None, ft_deltas=None, do_transfer=True, novel_neg_inf=False,
+                                want_similarity: Sequence[str] = ()):
+    dev = _need_cuda(delta_scores, proposal_deltas)
+    R = delta_scores.shape[0]
+    delta_scores, proposal_deltas = _c(delta_scores, _F32), _c(proposal_deltas, _F32)
+    cv = lambda t: None if t is None else _c(t, _F32)
+    vis_logits, weak_scores, ft_scores, ft_deltas = cv(vis_logits), cv(weak_scores), cv(ft_scores), cv(ft_deltas)
+    out_scores = torch.empty_like(delta_scores)
+    out_bbox = torch.empty_like(proposal_deltas)
+    sims = {h: (torch.empty((R, spec.Nn, spec.B), dtype=_F32, device=dev) if h in want_similarity else None)
+            for h in ("cls", "bbox", "seg")}
+    if R:
+        p = spec.params(R, do_transfer, novel_neg_inf)
+        check(lib().unit_similarity_transfer(ctypes.byref(p), _ptr(vis_logits), _ptr(spec.static.get("cls")),
+                                             _ptr(spec.static.get("bbox")), _ptr(spec.static.get("seg")),
+                                             _ptr(spec.base_i32), _ptr(spec.novel_i32), _ptr(spec.class_kind),
+                                             _ptr(delta_scores), _ptr(proposal_deltas), _ptr(weak_scores),
+                                             _ptr(ft_scores), _ptr(ft_deltas), _ptr(out_scores), _ptr(out_bbox),
+                                             _ptr(sims["cls"]), _ptr(sims["bbox"]), _ptr(sims["seg"]), _stream()),
+              "unit_similarity_transfer")
+    return out_scores, out_bbox, sims
+
+
+def similarity_transfer_backward(spec: TransferSpec, s_cls, s_bbox, g_scores, g_bbox, detach_transfer=False):
+    dev = _need_cuda(g_scores, g_bbox)
+    R = g_scores.shape[0]
+    g_scores, g_bbox = _c(g_scores, _F32), _c(g_bbox, _F32)
+    g_delta = torch.empty_like(g_scores)
+    g_pd = torch.empty_like(g_bbox)
+    if R:
+        p = spec.params(R, True, False)
+        check(lib().unit_similarity_transfer_bwd(ctypes.byref(p), _ptr(s_cls), _ptr(s_bbox), _ptr(spec.base_i32),
+                                                 _ptr(spec.novel_i32), _ptr(spec.class_kind), _ptr(g_scores),
+                                                 _ptr(g_bbox), int(bool(detach_transfer)), _ptr(g_delta), _ptr(g_pd),
+                                                 _stream()), "unit_similarity_transfer_bwd")
+    return g_delta, g_pd
+
+
+class _TransferFn(torch.autograd.Function):
+    """Autograd of the fused transfer w.r.t. (delta_scores, proposal_deltas, ft_scores, ft_deltas).
+
+    The similarity is treated as a constant (it is built from frozen weights in every shipped fine-tune YAML,
+    configs/VOC/FT/*/...-ft.yaml:6-9); a vis_logits tensor that requires grad is rejected.
+    """
+
+    @staticmethod
+    def forward(ctx, spec, vis_logits, delta_scores, proposal_deltas, weak_scores, ft_scores, ft_deltas, do_transfer,
+                novel_neg_inf, detach_transfer):
+        need_grad = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        want = ("cls", "bbox") if (need_grad and do_transfer and not detach_transfer) else ()
+        out_scores, out_bbox, sims = similarity_transfer_forward(spec, vis_logits, delta_scores, proposal_deltas,
+                                                                 weak_scores, ft_scores, ft_deltas, do_transfer,
+                                                                 novel_neg_inf, want)
+        ctx.spec, ctx.do_transfer, ctx.detach, ctx.neg_inf = spec, do_transfer, detach_transfer, novel_neg_inf
+        ctx.save_for_backward(*(t for t in (sims["cls"], sims["bbox"]) if t is not None))
+        ctx.has_ft = (ft_scores is not None, ft_deltas is not None)
+        return out_scores, out_bbox
+
+    @staticmethod
+    def backward(ctx, g_scores, g_bbox):
+        saved = ctx.saved_tensors
+        g_scores, g_bbox = g_scores.contiguous(), g_bbox.contiguous()
+        if ctx.neg_inf:
+            kind = ctx.spec.class_kind
+            g_scores = g_scores.clone()
+            g_scores[:, :-1][:, kind >= NOVEL_TAG] = 0
+        if ctx.do_transfer:
+            s_cls, s_bbox = (saved[0], saved[1]) if len(saved) == 2 else (None, None)
+            g_delta, g_pd = similarity_transfer_backward(ctx.spec, s_cls, s_bbox, g_scores, g_bbox,
+                                                         detach_transfer=ctx.detach or s_cls is None)
+        else:
+            g_delta, g_pd = g_scores, g_bbox
+        return (None, None, g_delta, g_pd, None, g_scores if ctx.has_ft[0] else None,
+                g_bbox if ctx.has_ft[1] else None, None, None, None)
+
+
+def similarity_transfer(spec: TransferSpec, vis_logits, delta_scores, proposal_deltas, weak_scores=None,
+                        ft_scores=None, ft_deltas=None, do_transfer=True, novel_neg_inf=False,
+                        detach_transfer=False):
+    if vis_logits is not None and vis_logits.requires_grad:
+        raise RuntimeError("similarity_transfer: gradients through the visual similarity are not implemented "
+                           "(it is computed from frozen weights in every shipped fine-tune config)")
+    return _TransferFn.apply(spec, vis_logits, delta_scores, proposal_deltas, weak_scores, ft_scores, ft_deltas,
+                             bool(do_transfer), bool(novel_neg_inf), bool(detach_transfer))
+
+
+# ------------------------------------------------------------------------------------------------- masks
+def mask_transfer(logits: torch.Tensor, s_seg: Optional[torch.Tensor], spec: TransferSpec,
+                  x_delta: Optional[torch.Tensor] = None, pred_classes: Optional[torch.Tensor] = None,
+                  want_logits: bool = False, want_probs: bool = True):
+    dev = _need_cuda(logits)
+    logits = _c(logits, _F32)
+    D, K, M1, M2 = logits.shape
+    MM = M1 * M2
+    out_logits = torch.empty_like(logits) if want_logits else None
+    out_probs = torch.empty((D, 1, M1, M2), dtype=_F32, device=dev) if want_probs else None
+    if D == 0:
+        return out_logits, out_probs
+    s = None if s_seg is None else _c(s_seg, _F32)
+    xd = None if x_delta is None else _c(x_delta, _F32)
+    pc = None if pred_classes is None else _c(pred_classes, torch.int64)
+    check(lib().unit_mask_transfer(_ptr(logits), _ptr(s), int(s is not None and s.dim() == 2), _ptr(spec.base_i32),
+                                   _ptr(spec.novel_i32), _ptr(spec.class_kind), _ptr(xd), _ptr(pc), _ptr(out_logits),
+                                   _ptr(out_probs), D, K, spec.B, spec.Nn, MM, _stream()), "unit_mask_transfer")
+    return out_logits, out_probs
+
+
+def mask_paste(masks: torch.Tensor, boxes: torch.Tensor, image_shape: Tuple[int, int], threshold: float = 0.5):
+    """[D2] paste_masks_in_image: masks [D,M,M] -> bool [D,H,W]."""
+    dev = _need_cuda(masks, boxes)
+    masks, boxes = _c(masks, _F32), _c(boxes, _F32)
+    D, M = masks.shape[0], masks.shape[-1]
+    h, w = int(image_shape[0]), int(image_shape[1])
+    out = torch.empty((D, h, w), dtype=torch.uint8, device=dev)
+    if D:
+        check(lib().unit_mask_paste(_ptr(masks), _ptr(boxes), D, M, h, w, float(threshold), _ptr(out), _stream()),
+              "unit_mask_paste")
+    return out.view(torch.bool)
