@@ -167,6 +167,7 @@ typedef struct {
   float wv_cls, wv_bbox, wv_seg;
   int norm_cls, norm_bbox, norm_seg;
   int do_transfer, novel_neg_inf;
+  int static_per_roi; /* bit h set: static_<head h> is [R,Nn,B] (an explicit per-RoI similarity) instead of [Nn,B] */
 } unit_transfer_params;
 int unit_similarity_transfer(const unit_transfer_params* p, const float* vis_logits, const float* static_cls,
                              const float* static_bbox, const float* static_seg, const int* base, const int* novel,

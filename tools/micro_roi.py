@@ -1,9 +1,10 @@
 """Micro-benchmark: ROIAlign fwd/bwd (ours vs torchvision CUDA) at the BASELINE shapes.  CUDA-event timed."""
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT,'tests'))
 import torch, torchvision
 from unit_b200 import ops
-from tests.conftest import random_boxes, seeded
+from conftest import random_boxes, seeded
 
 def timeit(fn, iters=20, warm=5, flush=None):
     for _ in range(warm): fn()

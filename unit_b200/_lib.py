@@ -20,7 +20,7 @@ class TransferParams(Structure):
         ("vis_threshold", c_float),
         ("wv_cls", c_float), ("wv_bbox", c_float), ("wv_seg", c_float),
         ("norm_cls", c_int), ("norm_bbox", c_int), ("norm_seg", c_int),
-        ("do_transfer", c_int), ("novel_neg_inf", c_int),
+        ("do_transfer", c_int), ("novel_neg_inf", c_int), ("static_per_roi", c_int),
     ]
 
 

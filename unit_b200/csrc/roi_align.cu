@@ -16,8 +16,10 @@
 //
 // Algorithmic bytes per image (fp32): C*H*W*4 + R*20 + R*C*196*4  (SURVEY.md section 8d).
 #include <cuda_bf16.h>
+#include <stdlib.h>
+#include <algorithm>
 
-#include "common.cuh"
+#include "roi_common.cuh"
 
 namespace unit {
 namespace roi {
@@ -42,80 +44,6 @@ struct RoiHeader {
   int mode;  // 0 = zero output, 1 = tables, 2 = direct (grid larger than MAXG)
   float start_w, start_h, bin_w, bin_h;
 };
-
-struct Geom {
-  float start_w, start_h, bin_w, bin_h;
-  int gw, gh;
-  float count;
-};
-
-// torchvision roi_align_kernel: same fp32 operation order (separate roundings).
-__device__ __forceinline__ Geom roi_geom(const float* roi, float scale, int ph, int pw, int sampling_ratio,
-                                         int aligned) {
-  Geom g;
-  const float offset = aligned ? 0.5f : 0.f;
-  g.start_w = __fsub_rn(__fmul_rn(roi[1], scale), offset);
-  g.start_h = __fsub_rn(__fmul_rn(roi[2], scale), offset);
-  const float end_w = __fsub_rn(__fmul_rn(roi[3], scale), offset);
-  const float end_h = __fsub_rn(__fmul_rn(roi[4], scale), offset);
-  float rw = __fsub_rn(end_w, g.start_w);
-  float rh = __fsub_rn(end_h, g.start_h);
-  if (!aligned) {
-    rw = fmaxf(rw, 1.f);
-    rh = fmaxf(rh, 1.f);
-  }
-  g.bin_w = __fdiv_rn(rw, (float)pw);
-  g.bin_h = __fdiv_rn(rh, (float)ph);
-  g.gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)pw));
-  g.gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rh, (float)ph));
-  const int c = g.gw * g.gh;
-  g.count = (float)(c > 1 ? c : 1);
-  return g;
-}
-
-// coordinate of sample `i` of bin `p`:  start + p*bin + (i + .5)*bin/grid   (left to right, fp32 each)
-__device__ __forceinline__ float sample_coord(float start, float bin, int p, int i, int grid) {
-  return __fadd_rn(__fadd_rn(start, __fmul_rn((float)p, bin)),
-                   __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), (float)grid));
-}
-
-// One axis of pre_calc_for_bilinear_interpolate: returns validity, low index and weights.
-__device__ __forceinline__ bool axis_tap(float v, int size, int& lo, int& hi, float& l, float& h) {
-  if (v < -1.0f || v > (float)size) {
-    lo = v < -1.0f ? 0 : size - 1;
-    hi = lo;
-    l = 0.f;
-    h = 0.f;
-    return false;
-  }
-  if (v <= 0.f) v = 0.f;
-  lo = (int)v;
-  if (lo >= size - 1) {
-    hi = lo = size - 1;
-    v = (float)lo;
-  } else {
-    hi = lo + 1;
-  }
-  l = __fsub_rn(v, (float)lo);
-  h = __fsub_rn(1.f, l);
-  return true;
-}
-
-// ---------------------------------------------------------------------------------------------- generic path
-// One thread per output element, taps read through L1/L2 (any P, C, roi order; used when the slab kernel's
-// preconditions do not hold).
-template <typename T>
-__device__ __forceinline__ float ldf(const T* p);
-template <>
-__device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
-template <>
-__device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
-template <typename T>
-__device__ __forceinline__ void stf(T* p, float v);
-template <>
-__device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
-template <>
-__device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
 template <typename T>
 __global__ void roi_align_fwd_generic(const T* __restrict__ feat, const float* __restrict__ rois, T* __restrict__ out,
@@ -256,101 +184,6 @@ struct VTaps {
   Tap a[GH > 0 ? GH : 1], b[GH > 0 ? GH : 1];
 };
 
-template <int GH>
-__device__ __forceinline__ void column(const float* __restrict__ plane, const VTaps<GH>& vt, const Tap* ya,
-                                       const Tap* yb, int gh, int col, float& ta, float& tb) {
-  if (GH > 0) {
-    ta = 0.f;
-    tb = 0.f;
-#pragma unroll
-    for (int i = 0; i < GH; ++i) {
-      ta = fmaf(vt.a[i].h, plane[vt.a[i].lo + col], ta);
-      ta = fmaf(vt.a[i].l, plane[vt.a[i].hi + col], ta);
-      tb = fmaf(vt.b[i].h, plane[vt.b[i].lo + col], tb);
-      tb = fmaf(vt.b[i].l, plane[vt.b[i].hi + col], tb);
-    }
-  } else {
-    ta = 0.f;
-    tb = 0.f;
-    for (int i = 0; i < gh; ++i) {
-      const Tap a = ya[i], b = yb[i];
-      ta = fmaf(a.h, plane[a.lo + col], ta);
-      ta = fmaf(a.l, plane[a.hi + col], ta);
-      tb = fmaf(b.h, plane[b.lo + col], tb);
-      tb = fmaf(b.l, plane[b.hi + col], tb);
-    }
-  }
-}
-
-// Forward task: thread = (channel plane, bin-row pair pp); writes out[0..13] = row 2pp, out[14..27] = row 2pp+1.
-template <int GH>
-__device__ __forceinline__ void fwd_task(const float* __restrict__ plane, int W, const RoiHeader& hdr,
-                                         const Tap* __restrict__ xtab, const Tap* __restrict__ ytab, int pp,
-                                         float* __restrict__ out) {
-  const int gw = hdr.gw, gh = hdr.gh;
-  const Tap* ya = ytab + (2 * pp) * gh;
-  const Tap* yb = ytab + (2 * pp + 1) * gh;
-  VTaps<GH> vt;
-  if (GH > 0) {
-#pragma unroll
-    for (int i = 0; i < GH; ++i) {
-      vt.a[i] = ya[i];
-      vt.b[i] = yb[i];
-    }
-  }
-  int cur = xtab[0].lo;
-  float lo_a, lo_b, hi_a, hi_b;
-  column<GH>(plane, vt, ya, yb, gh, cur, lo_a, lo_b);
-  column<GH>(plane, vt, ya, yb, gh, min(cur + 1, W - 1), hi_a, hi_b);
-  const float inv = hdr.inv_count;
-#pragma unroll
-  for (int pw = 0; pw < P; ++pw) {
-    float sa = 0.f, sb = 0.f;
-    const Tap* xs = xtab + pw * gw;
-    for (int ix = 0; ix < gw; ++ix) {
-      const Tap e = xs[ix];
-      while (e.lo > cur) {
-        ++cur;
-        lo_a = hi_a;
-        lo_b = hi_b;
-        column<GH>(plane, vt, ya, yb, gh, min(cur + 1, W - 1), hi_a, hi_b);
-      }
-      sa = fmaf(e.h, lo_a, sa);
-      sa = fmaf(e.l, hi_a, sa);
-      sb = fmaf(e.h, lo_b, sb);
-      sb = fmaf(e.l, hi_b, sb);
-    }
-    out[pw] = sa * inv;
-    out[P + pw] = sb * inv;
-  }
-}
-
-// Direct evaluation for RoIs whose sampling grid exceeds the table capacity (rare: side > 84 feature pixels).
-template <typename T>
-__device__ __noinline__ void fwd_task_direct(const float* __restrict__ plane, int H, int W, const RoiHeader& hdr,
-                                             int pp, T* __restrict__ out) {
-  for (int half = 0; half < 2; ++half) {
-    const int ph = 2 * pp + half;
-    for (int pw = 0; pw < P; ++pw) {
-      float acc = 0.f;
-      for (int iy = 0; iy < hdr.gh; ++iy) {
-        int ylo, yhi;
-        float ly, hy;
-        const bool vy = axis_tap(sample_coord(hdr.start_h, hdr.bin_h, ph, iy, hdr.gh), H, ylo, yhi, ly, hy);
-        for (int ix = 0; ix < hdr.gw; ++ix) {
-          int xlo, xhi;
-          float lx, hx;
-          const bool vx = axis_tap(sample_coord(hdr.start_w, hdr.bin_w, pw, ix, hdr.gw), W, xlo, xhi, lx, hx);
-          if (vy && vx)
-            acc += hy * (hx * plane[ylo * W + xlo] + lx * plane[ylo * W + xhi]) +
-                   ly * (hx * plane[yhi * W + xlo] + lx * plane[yhi * W + xhi]);
-        }
-      }
-      stf(out + half * P + pw, acc * hdr.inv_count);
-    }
-  }
-}
-
 template <typename T>
 __device__ __forceinline__ void load_slab(const T* __restrict__ src, float* __restrict__ slab, int HW, int ps,
                                           int tid, int nthreads);
@@ -407,35 +240,6 @@ __device__ __forceinline__ void load_slab<__nv_bfloat16>(const __nv_bfloat16* __
   }
 }
 
-__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-template <typename T>
-__device__ __forceinline__ void stage_write(T* dst, const float* v);  // 28 values
-template <>
-__device__ __forceinline__ void stage_write<float>(float* dst, const float* v) {
-  float4* d = reinterpret_cast<float4*>(dst);
-#pragma unroll
-  for (int i = 0; i < 7; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
-template <>
-__device__ __forceinline__ void stage_write<__nv_bfloat16>(__nv_bfloat16* dst, const float* v) {
-  uint2* d = reinterpret_cast<uint2*>(dst);
-#pragma unroll
-  for (int i = 0; i < 7; ++i) {
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[4 * i], v[4 * i + 1]);
-    __nv_bfloat162 p1 = __floats2bfloat162_rn(v[4 * i + 2], v[4 * i + 3]);
-    d[i] = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
-  }
-}
-
 struct FwdParams {
   const void* feat;
   const float* rois;
@@ -446,6 +250,7 @@ struct FwdParams {
   int sampling_ratio, aligned;
   int plane_stride;
   long long units_total;  // R * (C / CS)
+  int debug;              // experiments only (UNIT_ROI_DEBUG): bit0 skip compute, bit1 skip stores
 };
 
 // shared memory carve-up (bytes): slab | staging | xtab | ytab | headers
@@ -454,85 +259,6 @@ __host__ __device__ inline size_t smem_stage_bytes() { return (size_t)NB * CS * 
 inline size_t smem_bytes_total(int plane_stride, size_t stage_bytes) {
   return (size_t)CS * plane_stride * sizeof(float) + stage_bytes + 2 * (size_t)NB * MAXS * sizeof(Tap) +
          (size_t)NB * sizeof(RoiHeader) + 64;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(NTHREADS, 1) roi_align_fwd_slab(const FwdParams p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* slab = reinterpret_cast<float*>(smem_raw);
-  T* stage = reinterpret_cast<T*>(smem_raw + (size_t)CS * p.plane_stride * sizeof(float));
-  Tap* xtabs = reinterpret_cast<Tap*>(reinterpret_cast<unsigned char*>(stage) + smem_stage_bytes<T>());
-  Tap* ytabs = xtabs + NB * MAXS;
-  RoiHeader* hdrs = reinterpret_cast<RoiHeader*>(ytabs + NB * MAXS);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nslab = p.C / CS;
-  const int HW = p.H * p.W;
-  const T* feat = reinterpret_cast<const T*>(p.feat);
-  T* out = reinterpret_cast<T*>(p.out);
-
-  // contiguous unit range of this CTA
-  const long long u_begin = p.units_total * blockIdx.x / gridDim.x;
-  const long long u_end = p.units_total * (blockIdx.x + 1) / gridDim.x;
-  long long u = u_begin;
-  int n = 0;
-  while (u < u_end) {
-    while (n < p.N && (long long)p.img_off[n + 1] * nslab <= u) ++n;
-    if (n >= p.N) break;
-    const int r_base = p.img_off[n];
-    const int Rn = p.img_off[n + 1] - r_base;
-    const long long local = u - (long long)r_base * nslab;
-    const int k = (int)(local / Rn);
-    const int r0 = (int)(local - (long long)k * Rn);
-    const long long seg_end_u = min(u_end, (long long)r_base * nslab + (long long)(k + 1) * Rn);
-    const int r1 = r0 + (int)(seg_end_u - u);  // image-local RoI range [r0, r1)
-
-    __syncthreads();  // everyone is done with the previous slab
-    load_slab<T>(feat + ((long long)n * p.C + (long long)k * CS) * HW, slab, HW, p.plane_stride, tid, NTHREADS);
-    // (visibility of the slab is covered by the barrier after the first table build)
-
-    for (int rb = r0; rb < r1; rb += NB) {
-      const int nb = min(NB, r1 - rb);
-      if (warp < nb)
-        build_tables(p.rois + (long long)(r_base + rb + warp) * 5, p.scale, p.sampling_ratio, p.aligned, p.H, p.W,
-                     hdrs + warp, xtabs + warp * MAXS, ytabs + warp * MAXS, lane);
-      if (tid == 0) bulk_wait_read_all();  // staging buffer no longer being read by the previous bulk stores
-      __syncthreads();
-
-      const int b = warp >> 1;
-      const int pp = ((warp & 1) << 2) + (lane >> 3);
-      const int c = lane & 7;
-      if (b < nb && pp < P / 2) {
-        const RoiHeader hdr = hdrs[b];
-        const float* plane = slab + c * p.plane_stride;
-        T* dst = stage + ((size_t)b * CS + c) * (P * P) + pp * 2 * P;
-        if (hdr.mode == 2) {
-          fwd_task_direct<T>(plane, p.H, p.W, hdr, pp, dst);
-        } else {
-          float o[2 * P];
-          if (hdr.mode == 1) {
-            if (hdr.gh == 1) fwd_task<1>(plane, p.W, hdr, xtabs + b * MAXS, ytabs + b * MAXS, pp, o);
-            else if (hdr.gh == 2) fwd_task<2>(plane, p.W, hdr, xtabs + b * MAXS, ytabs + b * MAXS, pp, o);
-            else fwd_task<0>(plane, p.W, hdr, xtabs + b * MAXS, ytabs + b * MAXS, pp, o);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 2 * P; ++i) o[i] = 0.f;
-          }
-          stage_write<T>(dst, o);
-        }
-      }
-      fence_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        for (int i = 0; i < nb; ++i)
-          bulk_store(out + ((long long)(r_base + rb + i) * p.C + (long long)k * CS) * (P * P),
-                     stage + (size_t)i * CS * (P * P), (uint32_t)(CS * P * P * sizeof(T)));
-        bulk_commit();
-      }
-    }
-    u = seg_end_u;
-  }
-  if (tid == 0) bulk_wait_all();
 }
 
 // ---------------------------------------------------------------------------------------------- slab backward
@@ -743,16 +469,16 @@ static int launch_slab(bool backward, const void* a, const float* rois, void* b,
   p.aligned = aligned;
   p.plane_stride = plane_stride_host(H * W);
   p.units_total = (long long)R * (C / CS);
+  {
+    const char* dbg = getenv("UNIT_ROI_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   const size_t smem = smem_bytes_total(p.plane_stride, smem_stage_bytes<T>());
   roi_offsets_kernel<<<cdiv(R + 1, 256), 256, 0, st>>>(rois, R, N, img_off);
   UNIT_CHECK_LAUNCH("roi_offsets_kernel");
   if (!backward) {
-    UNIT_CUDA(cudaFuncSetAttribute(roi_align_fwd_slab<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long grid = p.units_total / 32;  // at least 32 units per CTA
-    if (grid < 1) grid = 1;
-    if (grid > sm_count()) grid = sm_count();
-    roi_align_fwd_slab<T><<<(int)grid, NTHREADS, smem, st>>>(p);
-    UNIT_CHECK_LAUNCH("roi_align_fwd_slab");
+    set_error("internal: forward goes through launch_fwd_slab2");
+    return UNIT_EINVAL;
   } else {
     UNIT_CUDA(cudaFuncSetAttribute(roi_align_bwd_slab<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     roi_align_bwd_slab<T><<<N * (C / CS), NTHREADS, smem, st>>>(p);
@@ -765,6 +491,10 @@ static bool slab_ok(int C, int H, int W, int PH, int PW, int rois_sorted, size_t
   if (!rois_sorted || PH != P || PW != P || (C % CS) != 0) return false;
   return smem_bytes_total(plane_stride_host(H * W), stage_bytes) <= 227 * 1024;
 }
+
+bool fwd_slab2_fits(int C, int H, int W, int dtype);
+int launch_fwd_slab2(const void* feat, const float* rois, void* out, int N, int C, int H, int W, int R, float scale,
+                     int sr, int aligned, int dtype, const int* img_off, cudaStream_t st);
 
 }  // namespace roi
 }  // namespace unit
@@ -784,18 +514,16 @@ int unit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, in
   if (R == 0) return UNIT_OK;
   UNIT_REQUIRE(feat && rois && out, "roi_align_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t stage = dtype == UNIT_F32 ? smem_stage_bytes<float>() : smem_stage_bytes<__nv_bfloat16>();
-  if (slab_ok(C, H, W, PH, PW, rois_sorted, stage) && N > 0) {
+  if (rois_sorted && PH == P && PW == P && N > 0 && fwd_slab2_fits(C, H, W, dtype)) {
     if (!workspace || workspace_bytes < unit_roi_align_workspace_bytes(N)) {
       set_error("roi_align_fwd: workspace too small (%zu < %zu)", workspace_bytes, unit_roi_align_workspace_bytes(N));
       return UNIT_EWORKSPACE;
     }
     UNIT_REQUIRE((((uintptr_t)out) & 15) == 0, "roi_align_fwd: out must be 16-byte aligned");
-    if (dtype == UNIT_F32)
-      return launch_slab<float>(false, feat, rois, out, N, C, H, W, R, spatial_scale, sampling_ratio, aligned,
-                                (int*)workspace, st);
-    return launch_slab<__nv_bfloat16>(false, feat, rois, out, N, C, H, W, R, spatial_scale, sampling_ratio, aligned,
-                                      (int*)workspace, st);
+    roi_offsets_kernel<<<cdiv(R + 1, 256), 256, 0, st>>>(rois, R, N, (int*)workspace);
+    UNIT_CHECK_LAUNCH("roi_offsets_kernel");
+    return launch_fwd_slab2(feat, rois, out, N, C, H, W, R, spatial_scale, sampling_ratio, aligned, dtype,
+                            (const int*)workspace, st);
   }
   const long long total = (long long)R * C * PH * PW;
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);

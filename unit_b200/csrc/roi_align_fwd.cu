@@ -1,0 +1,451 @@
+// ROIAlign forward, slab-resident kernel v2.
+//
+// Work unit = (image, 8-channel slab, RoI); a persistent CTA (one per SM) owns a contiguous range of units, keeps
+// the slab -- 8 full H x W channel planes, stored channel-PAIR interleaved as float2 -- resident in shared
+// memory, and its 12 warps pull RoIs of that slab from a shared counter.  A warp is a self-contained pipeline
+// (no CTA barrier in steady state):
+//   1. build the RoI's separable sampling tables in its private shared-memory area (fp32 operation order of the
+//      torchvision kernel, so floor / validity decisions are identical to the reference's);
+//   2. lane (q, cp), q = 0..6, cp = 0..3 computes output rows {q, q+7} of channels {2cp, 2cp+1}: it slides a window
+//      of vertically interpolated float2 values (one LDS.64 + one packed FFMA2 per tap serves both channels) along
+//      x, consuming the x-table in one rolled loop (advance / end-of-bin flags ride in the sign bits of the
+//      weights), and drops each finished bin into the warp's staging block;
+//   3. the [8 ch][14][14] block -- 6272 contiguous bytes of the NCHW output -- leaves as one TMA bulk store
+//      (cp.async.bulk.global.shared::cta); the next RoI's table build overlaps the store.
+// Every feature byte is read from HBM/L2 once per slab, every output byte is written once, fully coalesced.
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "roi_common.cuh"
+
+namespace unit {
+namespace roi {
+namespace v2 {
+
+constexpr int P = 14;
+constexpr int CS = 8;           // channels per slab
+constexpr int NPAIR = CS / 2;   // channel pairs
+constexpr int MAXG = 5;         // sampling grid per bin handled with tables (RoI side <= 70 feature px)
+constexpr int MAXS = P * MAXG;
+constexpr int NWARPS = 12;
+constexpr int NTHREADS = NWARPS * 32;
+
+struct __align__(16) YTap {
+  int lo;    // row * W of the lower tap
+  float h;   // its weight (hy)
+  float l;   // weight of the upper tap (ly)
+  int hi;    // row * W of the upper tap
+};
+
+struct __align__(16) Header {
+  int gw, gh;
+  float inv_count;
+  int mode;   // 0 zero output, 1 tables, 2 direct evaluation
+  int x0;     // first column of the sliding window
+  int nsamp;  // 14 * gw
+  float start_w, start_h;
+  float bin_w, bin_h;
+  int pad0, pad1;
+};
+
+// per-warp shared-memory area
+template <typename T>
+struct WarpArea {
+  Header hdr;
+  float2 xtab[MAXS + 2];  // (hx | ADV sign, lx | END sign)
+  YTap ytab[MAXS];
+  __align__(16) T stage[CS * P * P];
+};
+
+struct Params {
+  const void* feat;
+  const float* rois;
+  void* out;
+  const int* img_off;
+  int N, C, H, W, R;
+  float scale;
+  int sampling_ratio, aligned;
+  int pair_stride;  // float2 elements per channel-pair plane, == 1 (mod 16)
+  long long units_total;
+  int debug;
+};
+
+__device__ __forceinline__ float2 ffma2(float s, float2 v, float2 acc) {
+  unsigned long long a, b, c, d;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(s));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(v.x), "f"(v.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc.x), "f"(acc.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(d));
+  return r;
+}
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Build the tables of one RoI with the whole warp.
+template <typename T>
+__device__ __forceinline__ void build_tables(const float* __restrict__ roi, const Params& p, WarpArea<T>* wa,
+                                             int lane) {
+  const Geom g = roi_geom(roi, p.scale, P, P, p.sampling_ratio, p.aligned);
+  int mode = 1;
+  if (g.gw <= 0 || g.gh <= 0) mode = 0;
+  else if (g.gw > MAXG || g.gh > MAXG) mode = 2;
+  bool jump = false;
+  if (mode == 1) {
+    const int ns = P * g.gw;
+    for (int s = lane; s < ns; s += 32) {
+      int lo, hi, plo, phi;
+      float l, h, pl, phh;
+      axis_tap(sample_coord(g.start_w, g.bin_w, s / g.gw, s % g.gw, g.gw), p.W, lo, hi, l, h);
+      int adv = 0;
+      if (s > 0) {
+        axis_tap(sample_coord(g.start_w, g.bin_w, (s - 1) / g.gw, (s - 1) % g.gw, g.gw), p.W, plo, phi, pl, phh);
+        adv = lo - plo;
+      } else {
+        wa->hdr.x0 = lo;
+      }
+      jump |= (adv > 1 || adv < 0);
+      const bool end = (s % g.gw) == g.gw - 1;
+      float2 e;
+      e.x = adv ? -h : h;  // -0.0f keeps the flag when the weight is zero
+      e.y = end ? -l : l;
+      if (adv && h == 0.f) e.x = __uint_as_float(0x80000000u);
+      if (end && l == 0.f) e.y = __uint_as_float(0x80000000u);
+      wa->xtab[s] = e;
+    }
+    if (lane < 2) wa->xtab[ns + lane] = make_float2(0.f, 0.f);
+    for (int s = lane; s < P * g.gh; s += 32) {
+      YTap t;
+      axis_tap(sample_coord(g.start_h, g.bin_h, s / g.gh, s % g.gh, g.gh), p.H, t.lo, t.hi, t.l, t.h);
+      t.lo *= p.W;
+      t.hi *= p.W;
+      wa->ytab[s] = t;
+    }
+  }
+  // a sample step larger than one column can only come from fp32 rounding of bin/grid; evaluate such RoIs directly
+  if (__any_sync(0xffffffffu, jump)) mode = 2;
+  if (lane == 0) {
+    wa->hdr.gw = g.gw;
+    wa->hdr.gh = g.gh;
+    wa->hdr.inv_count = 1.f / g.count;
+    wa->hdr.mode = mode;
+    wa->hdr.nsamp = P * g.gw;
+    wa->hdr.start_w = g.start_w;
+    wa->hdr.start_h = g.start_h;
+    wa->hdr.bin_w = g.bin_w;
+    wa->hdr.bin_h = g.bin_h;
+  }
+}
+
+template <int GH>
+struct Taps {
+  YTap a[GH > 0 ? GH : 1], b[GH > 0 ? GH : 1];
+};
+
+// vertically interpolated float2 (channel pair) of column `col` for rows a and b
+template <int GH>
+__device__ __forceinline__ void column(const float2* __restrict__ pl, const Taps<GH>& t, const YTap* ya, const YTap* yb,
+                                       int gh, int col, float2& va, float2& vb) {
+  va = make_float2(0.f, 0.f);
+  vb = make_float2(0.f, 0.f);
+  if (GH > 0) {
+#pragma unroll
+    for (int i = 0; i < GH; ++i) {
+      va = ffma2(t.a[i].h, pl[t.a[i].lo + col], va);
+      va = ffma2(t.a[i].l, pl[t.a[i].hi + col], va);
+      vb = ffma2(t.b[i].h, pl[t.b[i].lo + col], vb);
+      vb = ffma2(t.b[i].l, pl[t.b[i].hi + col], vb);
+    }
+  } else {
+    for (int i = 0; i < gh; ++i) {
+      const YTap a = ya[i], b = yb[i];
+      va = ffma2(a.h, pl[a.lo + col], va);
+      va = ffma2(a.l, pl[a.hi + col], va);
+      vb = ffma2(b.h, pl[b.lo + col], vb);
+      vb = ffma2(b.l, pl[b.hi + col], vb);
+    }
+  }
+}
+
+template <typename T, int GH>
+__device__ __forceinline__ void task(const float2* __restrict__ pl, int W, const WarpArea<T>* wa, int q, int cp,
+                                     T* __restrict__ stage) {
+  const int gh = wa->hdr.gh;
+  const YTap* ya = wa->ytab + q * gh;
+  const YTap* yb = wa->ytab + (q + 7) * gh;
+  Taps<GH> t;
+  if (GH > 0) {
+#pragma unroll
+    for (int i = 0; i < GH; ++i) {
+      t.a[i] = ya[i];
+      t.b[i] = yb[i];
+    }
+  }
+  const int wm1 = W - 1;
+  int cur = wa->hdr.x0;
+  float2 lo_a, lo_b, hi_a, hi_b, nx_a, nx_b;
+  column<GH>(pl, t, ya, yb, gh, cur, lo_a, lo_b);
+  column<GH>(pl, t, ya, yb, gh, min(cur + 1, wm1), hi_a, hi_b);
+  column<GH>(pl, t, ya, yb, gh, min(cur + 2, wm1), nx_a, nx_b);
+  const float inv = wa->hdr.inv_count;
+  const int ns = wa->hdr.nsamp;
+  float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);
+  T* da0 = stage + (2 * cp) * (P * P) + q * P;  // row q of channel 2cp; channel 2cp+1 is P*P further
+  T* db0 = da0 + 7 * P;                         // row q+7
+  float2 e = wa->xtab[0];
+  for (int s = 0; s < ns; ++s) {
+    const float2 en = wa->xtab[s + 1];
+    const bool adv = __float_as_uint(e.x) >> 31;
+    const bool end = __float_as_uint(e.y) >> 31;
+    const float hx = fabsf(e.x), lx = fabsf(e.y);
+    if (adv) {
+      ++cur;
+      lo_a = hi_a;
+      lo_b = hi_b;
+      hi_a = nx_a;
+      hi_b = nx_b;
+      column<GH>(pl, t, ya, yb, gh, min(cur + 2, wm1), nx_a, nx_b);
+    }
+    acc_a = ffma2(hx, lo_a, acc_a);
+    acc_b = ffma2(hx, lo_b, acc_b);
+    acc_a = ffma2(lx, hi_a, acc_a);
+    acc_b = ffma2(lx, hi_b, acc_b);
+    if (end) {
+      stf(da0, acc_a.x * inv);
+      stf(da0 + P * P, acc_a.y * inv);
+      stf(db0, acc_b.x * inv);
+      stf(db0 + P * P, acc_b.y * inv);
+      ++da0;
+      ++db0;
+      acc_a = make_float2(0.f, 0.f);
+      acc_b = make_float2(0.f, 0.f);
+    }
+    e = en;
+  }
+}
+
+// direct evaluation (grid larger than MAXG or irregular sample steps): every lane fills its rows sample by sample
+template <typename T>
+__device__ __noinline__ void task_direct(const float2* __restrict__ pl, int H, int W, const Header& hdr, int q, int cp,
+                                         T* __restrict__ stage) {
+  for (int half = 0; half < 2; ++half) {
+    const int ph = q + 7 * half;
+    for (int pw = 0; pw < P; ++pw) {
+      float2 acc = make_float2(0.f, 0.f);
+      for (int iy = 0; iy < hdr.gh; ++iy) {
+        int ylo, yhi;
+        float ly, hy;
+        const bool vy = axis_tap(sample_coord(hdr.start_h, hdr.bin_h, ph, iy, hdr.gh), H, ylo, yhi, ly, hy);
+        for (int ix = 0; ix < hdr.gw; ++ix) {
+          int xlo, xhi;
+          float lx, hx;
+          const bool vx = axis_tap(sample_coord(hdr.start_w, hdr.bin_w, pw, ix, hdr.gw), W, xlo, xhi, lx, hx);
+          if (vy && vx) {
+            const float2 v1 = pl[ylo * W + xlo], v2 = pl[ylo * W + xhi], v3 = pl[yhi * W + xlo], v4 = pl[yhi * W + xhi];
+            acc.x += hy * (hx * v1.x + lx * v2.x) + ly * (hx * v3.x + lx * v4.x);
+            acc.y += hy * (hx * v1.y + lx * v2.y) + ly * (hx * v3.y + lx * v4.y);
+          }
+        }
+      }
+      stf(stage + (2 * cp) * (P * P) + ph * P + pw, acc.x * hdr.inv_count);
+      stf(stage + (2 * cp + 1) * (P * P) + ph * P + pw, acc.y * hdr.inv_count);
+    }
+  }
+}
+
+// slab loader: global planar [c][HW] -> shared [c/2][HW(+pad)][2]
+template <typename T>
+__device__ __forceinline__ void load_slab(const T* __restrict__ src, float* __restrict__ slab, int HW, int ps, int tid);
+template <>
+__device__ __forceinline__ void load_slab<float>(const float* __restrict__ src, float* __restrict__ slab, int HW,
+                                                 int ps, int tid) {
+  const int total = CS * HW;
+  if ((((uintptr_t)src) & 15) == 0 && (HW & 3) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int i = tid; i < (total >> 2); i += NTHREADS) {
+      const float4 v = __ldg(s4 + i);
+      const int e = i << 2;
+      const int c = e / HW, o = e - c * HW;
+      float* d = slab + ((size_t)(c >> 1) * ps + o) * 2 + (c & 1);
+      d[0] = v.x;
+      d[2] = v.y;
+      d[4] = v.z;
+      d[6] = v.w;
+    }
+  } else {
+    for (int e = tid; e < total; e += NTHREADS) {
+      const int c = e / HW, o = e - c * HW;
+      slab[((size_t)(c >> 1) * ps + o) * 2 + (c & 1)] = __ldg(src + e);
+    }
+  }
+}
+template <>
+__device__ __forceinline__ void load_slab<__nv_bfloat16>(const __nv_bfloat16* __restrict__ src,
+                                                         float* __restrict__ slab, int HW, int ps, int tid) {
+  const int total = CS * HW;
+  if ((((uintptr_t)src) & 15) == 0 && (HW & 7) == 0) {
+    const uint4* s8 = reinterpret_cast<const uint4*>(src);
+    for (int i = tid; i < (total >> 3); i += NTHREADS) {
+      const uint4 v = __ldg(s8 + i);
+      const int e = i << 3;
+      const int c = e / HW, o = e - c * HW;
+      float* d = slab + ((size_t)(c >> 1) * ps + o) * 2 + (c & 1);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        d[4 * k] = __uint_as_float(w[k] << 16);
+        d[4 * k + 2] = __uint_as_float(w[k] & 0xffff0000u);
+      }
+    }
+  } else {
+    for (int e = tid; e < total; e += NTHREADS) {
+      const int c = e / HW, o = e - c * HW;
+      slab[((size_t)(c >> 1) * ps + o) * 2 + (c & 1)] = __bfloat162float(src[e]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS, 1) roi_align_fwd_slab2(const Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* slab = reinterpret_cast<float*>(smem_raw);
+  const size_t slab_bytes = (size_t)NPAIR * p.pair_stride * sizeof(float2);
+  WarpArea<T>* areas = reinterpret_cast<WarpArea<T>*>(smem_raw + ((slab_bytes + 127) / 128) * 128);
+  __shared__ int s_next;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  WarpArea<T>* wa = areas + warp;
+  const int nslab = p.C / CS;
+  const int HW = p.H * p.W;
+  const T* feat = reinterpret_cast<const T*>(p.feat);
+  T* out = reinterpret_cast<T*>(p.out);
+  const int q = lane >> 2, cp = lane & 3;
+  const float2* pl = reinterpret_cast<const float2*>(slab) + (size_t)cp * p.pair_stride;
+
+  const long long u_begin = p.units_total * blockIdx.x / gridDim.x;
+  const long long u_end = p.units_total * (blockIdx.x + 1) / gridDim.x;
+  long long u = u_begin;
+  int n = 0;
+  while (u < u_end) {
+    while (n < p.N && (long long)p.img_off[n + 1] * nslab <= u) ++n;
+    if (n >= p.N) break;
+    const int r_base = p.img_off[n];
+    const int Rn = p.img_off[n + 1] - r_base;
+    const long long local = u - (long long)r_base * nslab;
+    const int k = (int)(local / Rn);
+    const int r0 = (int)(local - (long long)k * Rn);
+    const long long seg_end_u = min(u_end, (long long)r_base * nslab + (long long)(k + 1) * Rn);
+    const int r1 = r0 + (int)(seg_end_u - u);
+
+    __syncthreads();  // every warp has finished reading the previous slab
+    if (tid == 0) s_next = r0;
+    load_slab<T>(feat + ((long long)n * p.C + (long long)k * CS) * HW, slab, HW, p.pair_stride, tid);
+    __syncthreads();
+
+    while (true) {
+      int r = 0;
+      if (lane == 0) r = atomicAdd(&s_next, 1);
+      r = __shfl_sync(0xffffffffu, r, 0);
+      if (r >= r1) break;
+      build_tables<T>(p.rois + (long long)(r_base + r) * 5, p, wa, lane);
+      if (lane == 0) bulk_wait_read_all();  // the previous bulk store has drained this warp's staging block
+      __syncwarp();
+      if (!(p.debug & 1) && lane < 28) {
+        const int mode = wa->hdr.mode;
+        if (mode == 1) {
+          const int gh = wa->hdr.gh;
+          if (gh == 1) task<T, 1>(pl, p.W, wa, q, cp, wa->stage);
+          else if (gh == 2) task<T, 2>(pl, p.W, wa, q, cp, wa->stage);
+          else task<T, 0>(pl, p.W, wa, q, cp, wa->stage);
+        } else if (mode == 2) {
+          task_direct<T>(pl, p.H, p.W, wa->hdr, q, cp, wa->stage);
+        } else {
+          for (int i = 0; i < P; ++i) {
+            stf(wa->stage + (2 * cp) * (P * P) + q * P + i, 0.f);
+            stf(wa->stage + (2 * cp + 1) * (P * P) + q * P + i, 0.f);
+            stf(wa->stage + (2 * cp) * (P * P) + (q + 7) * P + i, 0.f);
+            stf(wa->stage + (2 * cp + 1) * (P * P) + (q + 7) * P + i, 0.f);
+          }
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0 && !(p.debug & 2)) {
+        bulk_store(out + ((long long)(r_base + r) * p.C + (long long)k * CS) * (P * P), wa->stage,
+                   (uint32_t)(CS * P * P * sizeof(T)));
+        bulk_commit();
+      }
+    }
+    u = seg_end_u;
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
+static int pair_stride_host(int HW) {
+  int s = HW;
+  while ((s & 15) != 1) ++s;
+  return s;
+}
+
+template <typename T>
+static size_t smem_total(int HW) {
+  const size_t slab_bytes = (size_t)NPAIR * pair_stride_host(HW) * sizeof(float2);
+  return ((slab_bytes + 127) / 128) * 128 + (size_t)NWARPS * sizeof(WarpArea<T>);
+}
+
+}  // namespace v2
+
+bool fwd_slab2_fits(int C, int H, int W, int dtype) {
+  if (C % v2::CS) return false;
+  const size_t need = dtype == UNIT_F32 ? v2::smem_total<float>(H * W) : v2::smem_total<__nv_bfloat16>(H * W);
+  return need <= 227 * 1024;
+}
+
+template <typename T>
+static int launch_t(const void* feat, const float* rois, void* out, int N, int C, int H, int W, int R, float scale,
+                    int sr, int aligned, const int* img_off, cudaStream_t st) {
+  v2::Params p;
+  p.feat = feat;
+  p.rois = rois;
+  p.out = out;
+  p.img_off = img_off;
+  p.N = N;
+  p.C = C;
+  p.H = H;
+  p.W = W;
+  p.R = R;
+  p.scale = scale;
+  p.sampling_ratio = sr;
+  p.aligned = aligned;
+  p.pair_stride = v2::pair_stride_host(H * W);
+  p.units_total = (long long)R * (C / v2::CS);
+  const char* dbg = getenv("UNIT_ROI_DEBUG");
+  p.debug = dbg ? atoi(dbg) : 0;
+  const size_t smem = v2::smem_total<T>(H * W);
+  UNIT_CUDA(cudaFuncSetAttribute(v2::roi_align_fwd_slab2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long grid = p.units_total / 48;  // at least 4 RoIs per warp
+  if (grid < 1) grid = 1;
+  if (grid > sm_count()) grid = sm_count();
+  v2::roi_align_fwd_slab2<T><<<(int)grid, v2::NTHREADS, smem, st>>>(p);
+  UNIT_CHECK_LAUNCH("roi_align_fwd_slab2");
+  return UNIT_OK;
+}
+
+int launch_fwd_slab2(const void* feat, const float* rois, void* out, int N, int C, int H, int W, int R, float scale,
+                     int sr, int aligned, int dtype, const int* img_off, cudaStream_t st) {
+  if (dtype == UNIT_F32) return launch_t<float>(feat, rois, out, N, C, H, W, R, scale, sr, aligned, img_off, st);
+  return launch_t<__nv_bfloat16>(feat, rois, out, N, C, H, W, R, scale, sr, aligned, img_off, st);
+}
+
+}  // namespace roi
+}  // namespace unit

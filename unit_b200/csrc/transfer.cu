@@ -39,10 +39,11 @@ __global__ void lingual_kernel(const float* __restrict__ emb, const int64_t* __r
   const float* en = emb + indexer[novel[n]] * D;
   for (int b = warp; b < B; b += nwarp) {
     const float* eb = emb + indexer[base[b]] * D;
-    float acc = 0.f;
-    for (int d = lane; d < D; d += 32) acc = fmaf(en[d], eb[d], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) s_raw[b] = acc;
+    // fp64 accumulation: exp() in the softmax amplifies the rounding of these |L| ~ 30 dot products to ~1e-5 relative
+    double acc = 0.0;
+    for (int d = lane; d < D; d += 32) acc += (double)en[d] * (double)eb[d];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_raw[b] = (float)acc;
   }
   __syncthreads();
   if (warp == 0) {
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(TT) similarity_transfer_kernel(const TransferA
     for (int h = 0; h < 3; ++h) {
       if (h == 2 && !a.out_s[2]) continue;  // the seg similarity is only materialised for the mask head
       for (int n = warp; n < Nn; n += nwarp) {
-        const float* st = a.stat[h] ? a.stat[h] + n * B : nullptr;
+        const float* st = a.stat[h] ? a.stat[h] + (((a.p.static_per_roi >> h) & 1) ? (long long)r * Nn * B : 0) + n * B : nullptr;
         float sum = 0.f;
         for (int b = lane; b < B; b += 32) sum += (st ? st[b] : 0.f) + wv[h] * s_v[b];
         sum = warp_sum(sum);

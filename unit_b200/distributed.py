@@ -1,0 +1,81 @@
+"""Multi-GPU plumbing of the RoI stage: one process per GPU, images sharded across ranks.
+
+The path has NO data-path collective: every op is per image.  Two exchanges exist at the edges:
+  * fine-tuning: ONE NCCL all-reduce per step over a single flat bucket that holds only the trainable RoI-head /
+    transfer parameter gradients (VOC-FT: cls_score_ft + bbox_pred_ft = 0.83 MB fp32), replacing DDP's generic
+    25 MB buckets (reference: DistributedDataParallel inside [D2] DefaultTrainer, engine/defaults.py:266-288);
+  * inference: a final gather of the <= 100 detections per image (reference: comm.gather, data/evaluators.py:159).
+Works with the ``nccl`` backend on GPUs and ``gloo`` on CPU (tests).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_items: int, rank: int, world_size: int) -> List[int]:
+    """Round-robin image sharding (image i -> rank i % world)."""
+    return list(range(rank, n_items, world_size))
+
+
+class FlatGradBucket:
+    """Pre-flattened gradient bucket: ``param.grad`` of every registered parameter is a view into one buffer, so
+    the backward kernels write straight into it and one all-reduce (average) covers the whole RoI head."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatGradBucket needs at least one trainable parameter")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, device=dev, dtype=dt)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * self.flat.element_size()
+
+    def zero_(self) -> None:
+        self.flat.zero_()
+
+    def all_reduce_mean(self, async_op: bool = False):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return None
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        if async_op:
+            return work
+        self.flat.div_(dist.get_world_size())
+        return None
+
+    def finish(self, work) -> None:
+        if work is not None:
+            work.wait()
+            self.flat.div_(dist.get_world_size())
+
+
+def gather_detections(boxes: torch.Tensor, scores: torch.Tensor, classes: torch.Tensor, counts: torch.Tensor,
+                      topk: int):
+    """Gather padded per-image detections from every rank onto all ranks.
+
+    boxes [n,topk,4], scores [n,topk], classes [n,topk] (int64), counts [n] (int32); every rank must hold the same n.
+    Returns lists (one entry per rank) of the same tensors."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [boxes], [scores], [classes], [counts]
+    ws = dist.get_world_size()
+    packed = torch.cat([boxes.reshape(boxes.shape[0], -1), scores, classes.to(scores.dtype),
+                        counts.to(scores.dtype)[:, None]], dim=1).contiguous()
+    out = [torch.empty_like(packed) for _ in range(ws)]
+    dist.all_gather(out, packed)
+    b, s, c, n = [], [], [], []
+    for t in out:
+        b.append(t[:, :4 * topk].reshape(-1, topk, 4))
+        s.append(t[:, 4 * topk:5 * topk])
+        c.append(t[:, 5 * topk:6 * topk].to(torch.int64))
+        n.append(t[:, 6 * topk].to(torch.int32))
+    return b, s, c, n

@@ -349,7 +349,7 @@ class TransferSpec:
 
     def __init__(self, num_classes: int, base: Sequence[int], novel: Sequence[int], dev,
                  static: Optional[dict] = None, wv: Optional[dict] = None, norm: Optional[dict] = None,
-                 vis_threshold: float = 0.0):
+                 vis_threshold: float = 0.0, static_per_roi: int = 0):
         self.K, self.B, self.Nn = int(num_classes), len(base), len(novel)
         self.base_i32 = _i32(base, dev)
         self.novel_i32 = _i32(novel, dev)
@@ -358,6 +358,7 @@ class TransferSpec:
         self.wv = dict(wv or {})
         self.norm = dict(norm or {})
         self.vis_threshold = float(vis_threshold)
+        self.static_per_roi = int(static_per_roi)
 
     def params(self, R: int, do_transfer: bool, novel_neg_inf: bool) -> TransferParams:
         g = lambda d, k, default: d.get(k, default)
@@ -365,7 +366,7 @@ class TransferSpec:
                               float(g(self.wv, "cls", 0.0)), float(g(self.wv, "bbox", 0.0)),
                               float(g(self.wv, "seg", 0.0)),
                               int(g(self.norm, "cls", 0)), int(g(self.norm, "bbox", 0)), int(g(self.norm, "seg", 0)),
-                              int(do_transfer), int(novel_neg_inf))
+                              int(do_transfer), int(novel_neg_inf), self.static_per_roi)
 
 
 def similarity_transfer_forward(spec: TransferSpec, vis_logits, delta_scores, proposal_deltas, weak_scores=None,

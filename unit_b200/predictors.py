@@ -1,0 +1,411 @@
+"""Box predictors behind ``FAST_RCNN_REGISTRY`` / ``WEAK_DETECTOR_FAST_RCNN_REGISTRY`` with the reference's class
+names, constructor arguments, ``forward`` keywords and state_dict keys
+(modeling/roi_heads/fast_rcnn.py:287-585, weak_detector_fast_rcnn.py:38-187, 270-351).
+
+What differs from the reference is the execution: the five-to-seven ``Linear`` layers of a forward are one packed
+GEMM, and everything after it (visual similarity, combination, base->novel transfer, weak scores, fine-tune terms)
+is ONE fused CUDA kernel (csrc/transfer.cu) instead of ~30 ATen launches.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import layers, ops
+from .layers import Box2BoxTransform, Matcher, fast_rcnn_inference
+from .registry import FAST_RCNN_REGISTRY, WEAK_DETECTOR_FAST_RCNN_REGISTRY, configurable
+from .structures import Boxes, Instances, ShapeSpec
+
+logger = logging.getLogger("unit_b200")
+
+
+def _freeze(module: nn.Module, layers_to_freeze: Sequence[str]) -> None:
+    """Freeze by first dotted component of the parameter name (fast_rcnn.py:353-358, roi_heads.py:166-171)."""
+    for name, param in module.named_parameters():
+        if any(layer == name.split(".")[0] for layer in layers_to_freeze):
+            param.requires_grad = False
+
+
+def _input_size(input_shape) -> int:
+    if isinstance(input_shape, int):
+        input_shape = ShapeSpec(channels=input_shape)
+    return input_shape.channels * (input_shape.width or 1) * (input_shape.height or 1)
+
+
+class FusedSimilarity:
+    """Lazy similarity: carries the mean OICR logits of the box-head features; the fused kernel turns them into
+    ``S[R,Nn,B]`` on the fly.  ``materialize`` returns the explicit dict the reference's
+    ``get_similarity_matrices`` returns (roi_heads.py:245-336)."""
+
+    def __init__(self, spec: ops.TransferSpec, vis_logits: Optional[torch.Tensor], heads: Sequence[str]):
+        self.spec = spec
+        self.vis_logits = vis_logits
+        self.heads = tuple(heads)
+        self._cache: Optional[Dict[str, torch.Tensor]] = None
+
+    def materialize(self) -> Dict[str, torch.Tensor]:
+        if self._cache is None:
+            R = self.vis_logits.shape[0] if self.vis_logits is not None else 1
+            K = self.spec.K
+            dev = self.spec.class_kind.device
+            zs = torch.zeros((R, K + 1), device=dev)
+            zb = torch.zeros((R, 4 * K), device=dev)
+            _, _, sims = ops.similarity_transfer_forward(self.spec, self.vis_logits, zs, zb, want_similarity=self.heads)
+            self._cache = {h: sims[h] for h in self.heads}
+        return self._cache
+
+
+@WEAK_DETECTOR_FAST_RCNN_REGISTRY.register()
+class WeakDetectorOutputsBase(nn.Module):
+    """OICR weak detector head (weak_detector_fast_rcnn.py:38-187).  In scope: ``evaluation`` (the mean of its three
+    refinement classifiers is both the weak score and the source of the visual similarity), ``predict_*`` /
+    ``inference`` and ``label_and_sample_proposals``.  The MIL / OICR / PCL training losses are out of scope
+     and raise."""
+
+    @configurable
+    def __init__(self, input_shape, *, box2box_transform, num_classes, cls_agnostic_bbox_reg=False, oicr_iter=3,
+                 freeze_layers=(), detector_temp=1.0, classifier_temp=1.0, regression_branch=False,
+                 proposal_matcher=None, test_score_thresh=0.0, test_nms_thresh=0.5, test_topk_per_image=100,
+                 oicr_regression_branch=False, base_classes=None, novel_classes=None, **unused):
+        super().__init__()
+        if regression_branch or oicr_regression_branch or oicr_iter <= 0:
+            raise NotImplementedError("only the shipped OICR configuration (OICR_ITER>0, no regression branches) "
+                                      "is implemented (configs/default_config.py:40-50)")
+        self.num_classes = num_classes
+        self.oicr_iter = oicr_iter
+        self.box_dim = len(box2box_transform.weights)
+        self.num_bbox_reg_classes = 1 if cls_agnostic_bbox_reg else num_classes
+        self.detector_temp, self.classifier_temp = detector_temp, classifier_temp
+        self.regression_branch = regression_branch
+        self.oicr_regression_branch = oicr_regression_branch
+        self.proposal_matcher = proposal_matcher
+        self.box2box_transform = box2box_transform
+        self.test_score_thresh = test_score_thresh
+        self.test_nms_thresh = test_nms_thresh
+        self.test_topk_per_image = test_topk_per_image
+        self.base_classes = torch.tensor(list(base_classes or [])).long()
+        self.novel_classes = torch.tensor(list(novel_classes or [])).long()
+        self.input_size = _input_size(input_shape)
+        self.classifier_stream = nn.Linear(self.input_size, num_classes)
+        self.detection_stream = nn.Linear(self.input_size, num_classes)
+        self.oicr_predictors = nn.ModuleList([nn.Linear(self.input_size, num_classes + 1) for _ in range(oicr_iter)])
+        for l in [self.classifier_stream, self.detection_stream, *self.oicr_predictors]:
+            nn.init.normal_(l.weight, std=0.01)
+            nn.init.constant_(l.bias, 0.0)
+        _freeze(self, freeze_layers)
+
+    @classmethod
+    def from_config(cls, cfg, input_shape):
+        wd = cfg.MODEL.ROI_HEADS.FAST_RCNN.WEAK_DETECTOR
+        return {
+            "input_shape": input_shape,
+            "box2box_transform": Box2BoxTransform(weights=cfg.MODEL.ROI_BOX_HEAD.BBOX_REG_WEIGHTS),
+            "num_classes": cfg.MODEL.ROI_HEADS.NUM_CLASSES,
+            "cls_agnostic_bbox_reg": cfg.MODEL.ROI_BOX_HEAD.CLS_AGNOSTIC_BBOX_REG,
+            "oicr_iter": wd.OICR_ITER,
+            "freeze_layers": cfg.MODEL.FREEZE_LAYERS.FAST_RCNN,
+            "detector_temp": wd.DETECTOR_TEMP,
+            "classifier_temp": wd.CLASSIFIER_TEMP,
+            "regression_branch": wd.REGRESSION_BRANCH,
+            "proposal_matcher": Matcher(cfg.MODEL.ROI_HEADS.IOU_THRESHOLDS, cfg.MODEL.ROI_HEADS.IOU_LABELS,
+                                        allow_low_quality_matches=False),
+            "test_score_thresh": cfg.MODEL.ROI_HEADS.SCORE_THRESH_TEST,
+            "test_nms_thresh": cfg.MODEL.ROI_HEADS.NMS_THRESH_TEST,
+            "test_topk_per_image": cfg.TEST.DETECTIONS_PER_IMAGE,
+            "oicr_regression_branch": wd.OICR_REGRESSION_BRANCH,
+            "base_classes": cfg.DATASETS.FEWSHOT.BASE_CLASSES_ID,
+            "novel_classes": cfg.DATASETS.FEWSHOT.NOVEL_CLASSES_ID,
+        }
+
+    # -- packed weights ---------------------------------------------------------------------------------
+    def mean_oicr_weight(self):
+        """mean_k(W_k x + b_k) == (mean_k W_k) x + mean_k b_k: the 3 refinement classifiers collapse to one."""
+        w = torch.stack([p.weight for p in self.oicr_predictors]).mean(0)
+        b = torch.stack([p.bias for p in self.oicr_predictors]).mean(0)
+        return w, b
+
+    def mean_logits(self, x: torch.Tensor) -> torch.Tensor:
+        w, b = self.mean_oicr_weight()
+        return F.linear(x, w, b)
+
+    def evaluation(self, x_weak: torch.Tensor):
+        """weak_detector_fast_rcnn.py:167-187: ([list of OICR logits], zeros box deltas), None."""
+        cls_output = [p(x_weak) for p in self.oicr_predictors]
+        bbox_output = x_weak.new_zeros((x_weak.size(0), self.num_bbox_reg_classes * self.box_dim))
+        return [cls_output, bbox_output], None
+
+    def forward(self, x_weak: torch.Tensor):
+        if self.training:
+            classifier_stream = self.classifier_stream(x_weak) / self.classifier_temp
+            detection_stream = self.detection_stream(x_weak) / self.detector_temp
+            oicr_scores = [p(x_weak) for p in self.oicr_predictors]
+            return [classifier_stream, detection_stream, oicr_scores, [], None, None], None
+        return self.evaluation(x_weak)
+
+    def losses(self, weak_predictions, weak_proposals, weak_targets):
+        raise NotImplementedError("MIL / OICR / PCL weak losses are outside the scoped RoI stage "
+                                  "(SURVEY.md section 2 row 3, section 8f rank 3)")
+
+    # -- inference (weak_detector_fast_rcnn.py:270-306) ---------------------------------------------------
+    def predict_boxes(self, predictions, proposals):
+        _, proposal_deltas = predictions
+        num = [len(p) for p in proposals]
+        boxes = layers.cat([p.proposal_boxes.tensor for p in proposals])
+        return self.box2box_transform.apply_deltas(proposal_deltas, boxes).split(num)
+
+    def predict_probs(self, predictions, proposals):
+        scores, _ = predictions
+        scores = torch.sum(torch.softmax(torch.stack(scores, 0), -1), 0)
+        return scores.split([len(p) for p in proposals], dim=0)
+
+    def inference(self, predictions, proposals, tta=False):
+        scores = self.predict_probs(predictions, proposals)
+        if tta:
+            return [torch.cat(scores, 0), predictions[1]], None
+        boxes = self.predict_boxes(predictions, proposals)
+        return fast_rcnn_inference(boxes, scores, [x.image_size for x in proposals], self.test_score_thresh,
+                                   self.test_nms_thresh, self.test_topk_per_image)
+
+    def label_and_sample_proposals(self, proposals, targets, return_match_vals=False):
+        """weak_detector_fast_rcnn.py:320-351: fused IoU + UniT Matcher, every proposal kept."""
+        res, matched, vals = layers.label_and_sample(
+            proposals, targets, num_classes=self.num_classes, batch_size_per_image=0, positive_fraction=0.0,
+            thresholds=self.proposal_matcher.user_thresholds, labels=self.proposal_matcher.labels, sample=False,
+            want_vals=True)
+        if return_match_vals:
+            return res, matched, vals
+        return res, matched
+
+
+@FAST_RCNN_REGISTRY.register()
+class SupervisedDetectorOutputsBase(nn.Module):
+    """fast_rcnn.py:292-468.  ``forward(x, novel_classes, base_classes, supervised_branch_x_weak=None, x_weak=None,
+    similarity=None) -> ([scores, bbox], weak_branch_return)``."""
+
+    KIND = "Base"
+
+    @configurable
+    def __init__(self, input_shape, *, box2box_transform, num_classes, test_score_thresh=0.0, test_nms_thresh=0.5,
+                 test_topk_per_image=100, cls_agnostic_bbox_reg=False, smooth_l1_beta=0.0,
+                 box_reg_loss_type="smooth_l1", loss_weight=1.0, weak_detector_head=None, regression_branch=False,
+                 terms=None, freeze_layers=(), embedding_path="", embeddings=None):
+        super().__init__()
+        if cls_agnostic_bbox_reg:
+            raise NotImplementedError("class-agnostic box regression is not used by any reference YAML")
+        self.num_classes = num_classes
+        self.terms = dict(terms or {})
+        self.box_dim = len(box2box_transform.weights)
+        self.num_bbox_reg_classes = num_classes
+        self.box2box_transform = box2box_transform
+        self.smooth_l1_beta = smooth_l1_beta
+        self.box_reg_loss_type = box_reg_loss_type
+        self.test_score_thresh = test_score_thresh
+        self.test_nms_thresh = test_nms_thresh
+        self.test_topk_per_image = test_topk_per_image
+        self.loss_weight = loss_weight
+        self.weak_detector_head = weak_detector_head
+        self.regression_branch = regression_branch
+        self.input_size = _input_size(input_shape)
+        self.cls_score_delta = nn.Linear(self.input_size, num_classes + 1)
+        self.bbox_pred_delta = nn.Linear(self.input_size, num_classes * self.box_dim)
+        nn.init.constant_(self.cls_score_delta.weight, 0.0)
+        nn.init.normal_(self.bbox_pred_delta.weight, std=0.001)
+        for l in (self.cls_score_delta, self.bbox_pred_delta):
+            nn.init.constant_(l.bias, 0.0)
+        if embeddings is None:
+            embeddings = torch.load(embedding_path, weights_only=False)["embeddings"]
+        self.embeddings = nn.Embedding.from_pretrained(embeddings.float(), freeze=True)
+        self._extra_init()
+        _freeze(self, freeze_layers)
+
+    def _extra_init(self) -> None:
+        pass
+
+    @classmethod
+    def from_config(cls, cfg, input_shape):
+        rh = cfg.MODEL.ROI_HEADS
+        return {
+            "input_shape": input_shape,
+            "box2box_transform": Box2BoxTransform(weights=cfg.MODEL.ROI_BOX_HEAD.BBOX_REG_WEIGHTS),
+            "num_classes": rh.NUM_CLASSES,
+            "cls_agnostic_bbox_reg": cfg.MODEL.ROI_BOX_HEAD.CLS_AGNOSTIC_BBOX_REG,
+            "smooth_l1_beta": cfg.MODEL.ROI_BOX_HEAD.SMOOTH_L1_BETA,
+            "test_score_thresh": rh.SCORE_THRESH_TEST,
+            "test_nms_thresh": rh.NMS_THRESH_TEST,
+            "test_topk_per_image": cfg.TEST.DETECTIONS_PER_IMAGE,
+            "box_reg_loss_type": cfg.MODEL.ROI_BOX_HEAD.BBOX_REG_LOSS_TYPE,
+            "loss_weight": {"loss_box_reg": cfg.MODEL.ROI_BOX_HEAD.BBOX_REG_LOSS_WEIGHT},
+            "weak_detector_head": WEAK_DETECTOR_FAST_RCNN_REGISTRY.get(rh.FAST_RCNN.WEAK_DETECTOR.NAME)(cfg,
+                                                                                                        input_shape),
+            "regression_branch": rh.FAST_RCNN.WEAK_DETECTOR.REGRESSION_BRANCH,
+            "terms": {"cls": rh.FINETUNE_TERMS.CLASSIFIER, "bbox": rh.FINETUNE_TERMS.BBOX,
+                      "seg": rh.FINETUNE_TERMS.MASK},
+            "embedding_path": rh.EMBEDDING_PATH,
+            "freeze_layers": cfg.MODEL.FREEZE_LAYERS.FAST_RCNN,
+        }
+
+    # -- similarity --------------------------------------------------------------------------------------
+    def get_similarity(self, base_classes, novel_classes, indexer):
+        """fast_rcnn.py:376-382: raw lingual similarity [Nn,B]."""
+        raw, _ = ops.lingual_similarity(self.embeddings.weight, indexer, base_classes, novel_classes)
+        return raw
+
+    # -- forward -------------------------------------------------------------------------------------------
+    def _ft_layers(self):
+        return None, None
+
+    def _linears(self, x: torch.Tensor):
+        """One packed GEMM for every Linear that reads ``x``: [delta | bbox | (ft cls | ft bbox)]."""
+        K1, K4 = self.num_classes + 1, self.num_classes * self.box_dim
+        ws = [self.cls_score_delta.weight, self.bbox_pred_delta.weight]
+        bs = [self.cls_score_delta.bias, self.bbox_pred_delta.bias]
+        ft_c, ft_b = self._ft_layers()
+        if ft_c is not None:
+            ws += [ft_c.weight, ft_b.weight]
+            bs += [ft_c.bias, ft_b.bias]
+        y = F.linear(x, torch.cat(ws, 0), torch.cat(bs, 0))
+        delta, pd = y[:, :K1], y[:, K1:K1 + K4]
+        fts = ftd = None
+        if ft_c is not None:
+            fts, ftd = y[:, K1 + K4:2 * K1 + K4], y[:, 2 * K1 + K4:]
+        return delta, pd, fts, ftd
+
+    def _transfer_mode(self, similarity):
+        """(do_transfer, novel_neg_inf, detach) for this predictor kind (fast_rcnn.py:401,427-428)."""
+        return (similarity is not None and not self.training), self.training, False
+
+    def forward(self, x, novel_classes, base_classes, supervised_branch_x_weak=None, x_weak=None, similarity=None):
+        if x is None:
+            raise NotImplementedError("the weak-image-only branch (x is None) belongs to the out-of-scope MIL/OICR "
+                                      "training path")
+        delta, pd, fts, ftd = self._linears(x)
+        with torch.no_grad():
+            weak_scores = self.weak_detector_head.mean_logits(x if supervised_branch_x_weak is None
+                                                              else supervised_branch_x_weak)
+        do_transfer, neg_inf, detach = self._transfer_mode(similarity)
+        spec, vis_logits = self._resolve_similarity(similarity, base_classes, novel_classes, x.device)
+        scores, bbox = ops.similarity_transfer(spec, vis_logits, delta, pd, weak_scores, fts, ftd, do_transfer,
+                                               neg_inf, detach)
+        weak_branch_return = None
+        if x_weak is not None:
+            weak_branch_return, _ = self.weak_detector_head(x_weak)
+        return [scores, bbox], weak_branch_return
+
+    def _resolve_similarity(self, similarity, base_classes, novel_classes, dev):
+        if isinstance(similarity, FusedSimilarity):
+            return similarity.spec, similarity.vis_logits
+        base, novel = base_classes.tolist(), novel_classes.tolist()
+        if similarity is None:
+            return self._plain_spec(base, novel, dev), None
+        # explicit matrices, exactly what the reference passes: [Nn,B] or [R,Nn,B] per head
+        static, per_roi = {}, 0
+        for i, h in enumerate(("cls", "bbox")):
+            static[h] = similarity[h]
+            if similarity[h].dim() > 2:
+                per_roi |= 1 << i
+        return ops.TransferSpec(self.num_classes, base, novel, dev, static, static_per_roi=per_roi), None
+
+    def _plain_spec(self, base, novel, dev):
+        key = (tuple(base), tuple(novel), str(dev))
+        cache = self.__dict__.setdefault("_spec_cache", {})
+        if key not in cache:
+            cache[key] = ops.TransferSpec(self.num_classes, base, novel, dev)
+        return cache[key]
+
+    # -- losses / inference --------------------------------------------------------------------------------
+    def losses(self, predictions, proposals, weak_predictions=None, weak_proposals=None, weak_targets=None,
+               train_only_weak=False):
+        """fast_rcnn.py:435-453: [D2] FastRCNNOutputs.losses (softmax CE + smooth-L1 on get_deltas)."""
+        if weak_predictions is not None:
+            return self.weak_detector_head.losses(weak_predictions, weak_proposals, weak_targets)
+        if train_only_weak:
+            return {}
+        scores, proposal_deltas = predictions
+        gt_classes = layers.cat([p.gt_classes for p in proposals])
+        prop = layers.cat([p.proposal_boxes.tensor for p in proposals])
+        gt_boxes = layers.cat([p.gt_boxes.tensor for p in proposals])
+        loss_cls = F.cross_entropy(scores, gt_classes, reduction="mean")
+        bg = scores.shape[1] - 1
+        fg_inds = layers.nonzero_tuple((gt_classes >= 0) & (gt_classes < bg))[0]
+        cols = self.box_dim * gt_classes[fg_inds][:, None] + torch.arange(self.box_dim, device=scores.device)
+        if self.box_reg_loss_type != "smooth_l1":
+            raise NotImplementedError("only the smooth_l1 box loss is used by the reference YAMLs")
+        target = self.box2box_transform.get_deltas(prop, gt_boxes)[fg_inds]
+        pred = proposal_deltas[fg_inds[:, None], cols]
+        n = torch.abs(pred - target)
+        if self.smooth_l1_beta < 1e-5:
+            loss_box = n.sum()
+        else:
+            b = self.smooth_l1_beta
+            loss_box = torch.where(n < b, 0.5 * n ** 2 / b, n - 0.5 * b).sum()
+        return {"loss_cls": loss_cls, "loss_box_reg": loss_box / max(gt_classes.numel(), 1)}
+
+    def predict_probs(self, predictions, proposals):
+        scores, _ = predictions
+        probs, _ = ops.softmax_decode(scores, None, None, want_boxes=False)
+        return probs.split([len(p) for p in proposals], dim=0)
+
+    def predict_boxes(self, predictions, proposals):
+        if not len(proposals):
+            return []
+        _, proposal_deltas = predictions
+        boxes = layers.cat([p.proposal_boxes.tensor for p in proposals])
+        return self.box2box_transform.apply_deltas(proposal_deltas, boxes).split([len(p) for p in proposals])
+
+    def inference(self, predictions, proposals, tta=False):
+        """fast_rcnn.py:455-468: softmax + decode in one launch, then batched filter + NMS."""
+        scores, proposal_deltas = predictions
+        n = [len(p) for p in proposals]
+        if tta:
+            probs, _ = ops.softmax_decode(scores, None, None, want_boxes=False)
+            return [probs, predictions[1]], None
+        boxes_in = layers.cat([p.proposal_boxes.tensor for p in proposals])
+        probs, boxes = ops.softmax_decode(scores, proposal_deltas, boxes_in, self.box2box_transform.weights,
+                                          self.box2box_transform.scale_clamp)
+        return fast_rcnn_inference(boxes.split(n), probs.split(n), [x.image_size for x in proposals],
+                                   self.test_score_thresh, self.test_nms_thresh, self.test_topk_per_image)
+
+
+@FAST_RCNN_REGISTRY.register()
+class SupervisedDetectorOutputsFineTune(SupervisedDetectorOutputsBase):
+    """fast_rcnn.py:470-533: adds zero-initialised ``cls_score_ft`` / ``bbox_pred_ft``; transfer applied in
+    training too."""
+
+    KIND = "FineTune"
+
+    def _extra_init(self) -> None:
+        self.cls_score_ft = nn.Linear(self.input_size, self.num_classes + 1)
+        self.bbox_pred_ft = nn.Linear(self.input_size, self.num_bbox_reg_classes * self.box_dim)
+        for l in (self.cls_score_ft, self.bbox_pred_ft):
+            nn.init.constant_(l.weight, 0.0)
+            nn.init.constant_(l.bias, 0.0)
+
+    def _ft_layers(self):
+        return self.cls_score_ft, self.bbox_pred_ft
+
+    def _transfer_mode(self, similarity):
+        return similarity is not None, False, False
+
+
+@FAST_RCNN_REGISTRY.register()
+class SupervisedDetectorOutputsWeakFineTune(SupervisedDetectorOutputsBase):
+    """fast_rcnn.py:535-585: transfer always applied, transferred part detached from the graph (:566,575)."""
+
+    KIND = "WeakFineTune"
+
+    def _transfer_mode(self, similarity):
+        return similarity is not None, False, True
+
+
+@FAST_RCNN_REGISTRY.register()
+class WeakDetectorOutputsBaseWrapper(WeakDetectorOutputsBase):
+    """fast_rcnn.py:287-290."""
+
+
+def build_fastrcnn_head(cfg, input_shape):
+    """fast_rcnn.py:587-589."""
+    return FAST_RCNN_REGISTRY.get(cfg.MODEL.ROI_HEADS.FAST_RCNN.NAME)(cfg, input_shape)
