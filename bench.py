@@ -1,0 +1,469 @@
+#!/usr/bin/env python
+"""bench.py -- RoI-stage images/sec (BASELINE.json metric) for the B200-native UniT RoI stage.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype f32|bf16]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], per GPU; weak scaling -- every rank gets the same amount of work):
+VOC R101-C4 split-1 10-shot FINE-TUNE RoI-head train step on 2 synthetic 800x1333 images:
+  res4 features [2,1024,50,84]; 2000 RPN proposals + G GT boxes per image -> fused IoU+Matcher -> fg/bg sampling of
+  512 RoIs/image -> ROIAlign forward [1024,1024,14,14] -> (res5 box head: OUT OF SCOPE, replaced by fixed synthetic
+  [1024,2048] box features and a fixed synthetic dL/dpooled) -> packed predictor GEMM -> fused similarity + base->novel
+  transfer -> CE + smooth-L1 -> backward to cls_score_ft / bbox_pred_ft -> ROIAlign backward -> (N>1) one NCCL
+  all-reduce of the flat 0.83 MB gradient bucket.
+One JSON line on stdout (rank 0).  `value` = images/sec with inputs resident in HBM; `e2e` = the same step called with
+HOST (pinned) buffers: H2D of features/proposals/GT and D2H of the loss inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_IMG = 2           # images per GPU per step
+P_RPN = 2000        # RPN proposals per image in training ([D2] POST_NMS_TOPK_TRAIN)
+BATCH = 512         # sampled RoIs per image
+C, H, W = 1024, 50, 84
+IMG_HW = (800, 1333)
+K_CLASSES = 20
+FEAT_DIM = 2048
+N_SETS = 4          # rotating input sets: 4 x 34.4 MB features (+ 822 MB of ROIAlign output per step) > 126 MB L2
+
+
+def _seeded(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _boxes(n, h, w, g, min_size=16.0):
+    cx = torch.rand(n, generator=g) * w
+    cy = torch.rand(n, generator=g) * h
+    bw = min_size + 0.6 * w * torch.rand(n, generator=g) ** 2
+    bh = min_size + 0.6 * h * torch.rand(n, generator=g) ** 2
+    b = torch.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
+    b[:, 0::2] = b[:, 0::2].clamp(0, w)
+    b[:, 1::2] = b[:, 1::2].clamp(0, h)
+    return b
+
+
+def make_inputs(seed, dtype=torch.float32):
+    """Synthetic inputs of SURVEY.md section 8d (host tensors)."""
+    g = _seeded(seed)
+    feats = torch.randn(N_IMG, C, H, W, generator=g).to(dtype)
+    props, gts, gcls = [], [], []
+    for _ in range(N_IMG):
+        n_gt = int(torch.randint(1, 9, (1,), generator=g))
+        gt = _boxes(n_gt, IMG_HW[0], IMG_HW[1], g, 32.0)
+        pb = _boxes(P_RPN, IMG_HW[0], IMG_HW[1], g, 16.0)
+        k = P_RPN // 4  # 25 % of the proposals are GT boxes jittered by <= 10 % so that positives exist
+        pb[:k] = gt[torch.randint(0, n_gt, (k,), generator=g)] * (1 + 0.1 * (torch.rand(k, 4, generator=g) - 0.5))
+        pb[:, 0::2] = pb[:, 0::2].clamp(0, IMG_HW[1])
+        pb[:, 1::2] = pb[:, 1::2].clamp(0, IMG_HW[0])
+        props.append(pb)
+        gts.append(gt)
+        gcls.append(torch.randint(0, K_CLASSES, (n_gt,), generator=g))
+    return feats, props, gts, gcls
+
+
+def build_head(device):
+    from unit_b200 import d2compat  # noqa: F401
+    from unit_b200.config import load_cfg
+    from unit_b200.registry import ROI_BOX_HEAD_REGISTRY
+    from unit_b200.roi_heads import build_roi_heads
+    from unit_b200.structures import ShapeSpec
+
+    class OutOfScopeBoxHead(torch.nn.Module):
+        """Placeholder for Res5BoxHead (stock cuDNN convs, out of scope): contributes no parameters or work."""
+
+        def __init__(self, cfg, input_shape):
+            super().__init__()
+
+        @property
+        def output_shape(self):
+            return ShapeSpec(channels=FEAT_DIM, height=1, width=1)
+
+    if "OutOfScopeBoxHead" not in ROI_BOX_HEAD_REGISTRY:
+        ROI_BOX_HEAD_REGISTRY._do_register("OutOfScopeBoxHead", OutOfScopeBoxHead)
+    cfg = load_cfg(os.path.join(ROOT, "configs", "voc_split1_ft.yaml"),
+                   ["MODEL.ROI_BOX_HEAD.NAME", "OutOfScopeBoxHead", "MODEL.ROI_HEADS.EMBEDDING_PATH",
+                    os.path.join(ROOT, "tests", "golden", "glove_mean.pt")])
+    head = build_roi_heads(cfg, {"res4": ShapeSpec(channels=C, stride=16)})
+    g = _seeded(4242)
+    with torch.no_grad():  # the reference's inits x20 so the softmax is not flat; FT weights N(0, 0.01^2) not zeros
+        for name, p in sorted(head.named_parameters()):
+            if "embeddings" in name:
+                continue
+            std = 0.001 if ("bbox_pred_delta" in name and name.endswith("weight")) else 0.01
+            if name.endswith("bias"):
+                p.zero_()
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * std * (1.0 if "_ft" in name else 20.0))
+    return head.to(device).train()
+
+
+class Workload:
+    def __init__(self, device, dtype, rank):
+        from unit_b200.distributed import FlatGradBucket
+        from unit_b200.stage import RoIStage
+        from unit_b200.structures import Boxes, Instances
+
+        self.device, self.dtype = device, dtype
+        self.Boxes, self.Instances = Boxes, Instances
+        self.head = build_head(device)
+        self.head.sampling_generator = _seeded(1000 + rank)
+        self.bucket = FlatGradBucket([p for p in self.head.parameters() if p.requires_grad])
+        g = _seeded(77 + rank)
+        R = N_IMG * BATCH
+        self.x = torch.relu(torch.randn(R, FEAT_DIM, generator=g)).to(device)
+        self.xw = torch.relu(torch.randn(R, FEAT_DIM, generator=g)).to(device)
+        self.grad_pooled = torch.randn(R, C, 14, 14, generator=g).to(dtype).to(device)
+        self.stage = RoIStage(self.head, lambda pooled: (self.x, self.xw), self.bucket)
+        self.host_sets = [make_inputs(2000 + 10 * rank + s, dtype) for s in range(N_SETS)]
+        self.pinned = [(f.pin_memory(), [p.pin_memory() for p in pr], [t.pin_memory() for t in gt],
+                        [c.pin_memory() for c in gc]) for (f, pr, gt, gc) in self.host_sets]
+        self.dev_sets = [self._to_device(s, False) for s in self.host_sets]
+
+    def _to_device(self, s, non_blocking):
+        f, pr, gt, gc = s
+        dev = self.device
+        feats = f.to(dev, non_blocking=non_blocking)
+        props = [self.Instances(IMG_HW, proposal_boxes=self.Boxes(p.to(dev, non_blocking=non_blocking)),
+                                objectness_logits=torch.zeros(len(p), device=dev)) for p in pr]
+        tgts = [self.Instances(IMG_HW, gt_boxes=self.Boxes(t.to(dev, non_blocking=non_blocking)),
+                               gt_classes=c.to(dev, non_blocking=non_blocking)) for t, c in zip(gt, gc)]
+        return feats, props, tgts
+
+    def step(self, i):
+        feats, props, tgts = self.dev_sets[i % N_SETS]
+        return self.stage.train_step(feats, props, tgts, grad_pooled_fn=lambda pooled: self.grad_pooled)
+
+    def step_e2e(self, i):
+        feats, props, tgts = self._to_device(self.pinned[i % N_SETS], True)
+        loss, _ = self.stage.train_step(feats, props, tgts, grad_pooled_fn=lambda pooled: self.grad_pooled)
+        return float(loss.item())  # device -> host read of the step's result
+
+    def h2d_bytes(self):
+        f, pr, gt, gc = self.host_sets[0]
+        return int(f.numel() * f.element_size() + sum(p.numel() * 4 for p in pr) + sum(t.numel() * 4 for t in gt) +
+                   sum(c.numel() * 8 for c in gc))
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                parts = [x.strip() for x in out.split(",")]
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+                for n, v in zip(names, parts[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def time_kernel(fn, iters, flush):
+    """Average device time (ms) of one launch on the current stream, L2 flushed between launches."""
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        e.synchronize()
+        ts.append(s.elapsed_time(e))
+    return sum(ts) / len(ts)
+
+
+# ------------------------------------------------------------------------------------------------- CPU reference
+def cpu_reference_step(host_set, weights, head_meta, gen, x, xw, grad_pooled, roi_sample=None):
+    """The reference's CPU path for the same step, restated in oracle/ (torchvision CPU ROIAlign kernels +
+    Detectron2 glue + UniT transfer).  ``roi_sample`` bounds the ROIAlign part to that many RoIs per image."""
+    from oracle import unit_ref
+    from oracle.d2.ops import Box2BoxTransform, MatcherWithVals, subsample_labels
+    from oracle.d2.structures import Boxes, pairwise_iou
+    import torch.nn.functional as F
+
+    feats, props, gts, gcls = host_set
+    t0 = time.perf_counter()
+    matcher = MatcherWithVals([0.5], [0, 1])
+    s_boxes, s_cls, s_gt = [], [], []
+    for pb, gt, gc in zip(props, gts, gcls):
+        allp = torch.cat([pb, gt])
+        m, l, _ = matcher(pairwise_iou(Boxes(gt), Boxes(allp)))
+        cls = gc[m]
+        cls[l == 0] = K_CLASSES
+        pos, neg = subsample_labels(cls, BATCH, 0.25, K_CLASSES, generator=gen)
+        idx = torch.cat([pos, neg])
+        s_boxes.append(allp[idx])
+        s_cls.append(cls[idx])
+        s_gt.append(gt[m[idx]])
+    t_label = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    n_roi = BATCH if roi_sample is None else roi_sample
+    rois = torch.cat([torch.cat([torch.full((n_roi, 1), float(i)), b[:n_roi]], 1) for i, b in enumerate(s_boxes)])
+    f32 = feats.float()
+    pooled = torch.ops.torchvision.roi_align(f32, rois, 1 / 16, 14, 14, 0, True)
+    gfeat = torch.ops.torchvision._roi_align_backward(grad_pooled[: rois.shape[0]].float(), rois, 1 / 16, 14, 14,
+                                                      N_IMG, C, H, W, 0, True)
+    t_roi = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    base, novel, idx = head_meta
+    w = dict(weights)
+    for k in ("cls_score_ft.weight", "cls_score_ft.bias", "bbox_pred_ft.weight", "bbox_pred_ft.bias"):
+        w[k] = w[k].clone().requires_grad_(True)
+    L = unit_ref.lingual_similarity(w["embeddings.weight"], idx, base, novel)
+    V = unit_ref.visual_similarity(unit_ref.oicr_mean_logits(x, w), base, 0.02)
+    sim = unit_ref.similarity_matrices(L, V, {"cls": ["lingual", "visual"], "bbox": ["lingual", "visual"]}, 5, 15)
+    scores, bbox = unit_ref.predictor_forward(x, xw, w, sim, base, novel, K_CLASSES, kind="FineTune", training=True)
+    gt_classes = torch.cat(s_cls)
+    loss_cls = F.cross_entropy(scores, gt_classes)
+    fg = ((gt_classes >= 0) & (gt_classes < K_CLASSES)).nonzero().squeeze(1)
+    cols = 4 * gt_classes[fg][:, None] + torch.arange(4)
+    tgt = Box2BoxTransform((10.0, 10.0, 5.0, 5.0)).get_deltas(torch.cat(s_boxes), torch.cat(s_gt))[fg]
+    loss = loss_cls + (bbox[fg[:, None], cols] - tgt).abs().sum() / gt_classes.numel()
+    loss.backward()
+    t_pred = time.perf_counter() - t0
+    return float(loss), t_label, t_roi, t_pred, pooled, gfeat
+
+
+def cpu_workload(rank=0):
+    head = build_head(torch.device("cpu"))
+    w = {k: v.detach().clone() for k, v in head.box_predictor.state_dict().items()}
+    meta = (head._base_classes_tensor, head._novel_classes_tensor, head._coco_indexer_tensor)
+    g = _seeded(77 + rank)
+    R = N_IMG * BATCH
+    x = torch.relu(torch.randn(R, FEAT_DIM, generator=g))
+    xw = torch.relu(torch.randn(R, FEAT_DIM, generator=g))
+    gp = torch.randn(R, C, 14, 14, generator=g)
+    return w, meta, x, xw, gp
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: torchvision CPU kernels +
+    restated Detectron2 / UniT glue) on all host cores.  Each step runs label/sample + transfer on the full
+    workload and ROIAlign fwd+bwd on a bounded sample of RoIs, scaled to the full 512 RoIs/image."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w, meta, x, xw, gp = cpu_workload()
+    sets = [make_inputs(2000 + s) for s in range(2)]
+    roi_sample = 32
+    gen = _seeded(1000)
+    for i in range(max(args.warmup, 1)):
+        cpu_reference_step(sets[i % 2], w, meta, gen, x, xw, gp, roi_sample)
+    est = []
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        _, tl, tr, tp, _, _ = cpu_reference_step(sets[i % 2], w, meta, gen, x, xw, gp, roi_sample)
+        est.append(tl + tp + tr * (BATCH / roi_sample))
+    t_wall = time.perf_counter() - t_wall
+    ms = 1000.0 * sum(est) / len(est)
+    value = N_IMG / (ms / 1000.0)
+    sample = (f"per step: label+sample and transfer+loss+backward on the full 2x512-RoI workload, ROIAlign fwd+bwd "
+              f"on {roi_sample} of 512 RoIs/image and scaled x{BATCH // roi_sample}; wall {t_wall:.1f}s for "
+              f"{args.steps} steps")
+    line = {
+        "impl": "reference", "metric": "RoI-stage images/sec (VOC R101-C4 FT train step)", "value": value,
+        "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config("f32"),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(dtype):
+    return {
+        "workload": "BASELINE.json configs[1]: VOC-RCNN-101-C4-split1 10-shot fine-tune RoI-head train step, "
+                    "2 synthetic 800x1333 images per GPU (16 images on 8 GPUs), res4 [2,1024,50,84], 2000 proposals "
+                    "+ GT per image -> 512 sampled RoIs/image, 15 base + 5 novel classes",
+        "images_per_gpu": N_IMG, "rois_per_image": BATCH, "proposals_per_image": P_RPN, "io_dtype": dtype,
+        "box_head": "res5 excluded (stock PyTorch, out of scope): fixed synthetic [1024,2048] box features and "
+                    "fixed synthetic dL/dpooled feed the in-scope kernels",
+        "l2": f"inputs rotate over {N_SETS} sets; 137 MB of features + 822 MB ROIAlign output per step exceed the "
+              "126 MB L2",
+        "parallelism": "images sharded across GPUs, no data-path collective; one NCCL all-reduce of the flat "
+                       "0.83 MB cls_score_ft/bbox_pred_ft gradient bucket per step",
+    }
+
+
+# ------------------------------------------------------------------------------------------------- main arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    from unit_b200 import _lib, ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the "
+                         "CPU baseline")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    wl = Workload(device, dtype, rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            fn(i)
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(args.warmup):
+        wl.step(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    total_ms = timed(wl.step, args.steps)
+    launches = _lib.launch_count() - launches0
+    for i in range(max(args.warmup // 2, 1)):
+        wl.step_e2e(i)
+    e2e_ms = timed(wl.step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # dominant kernels, timed alone with CUDA events on the launching stream (L2 flushed between launches)
+    roofline = None
+    kernel_ms = {}
+    if rank == 0:
+        feats, props, tgts = wl.dev_sets[0]
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+        g = _seeded(5)
+        rois = torch.cat([torch.cat([torch.full((BATCH, 1), float(i)), _boxes(BATCH, IMG_HW[0], IMG_HW[1], g)], 1)
+                          for i in range(N_IMG)]).to(device)
+        es = 2 if dtype == torch.bfloat16 else 4
+        alg_bytes = N_IMG * C * H * W * es + N_IMG * BATCH * 20 + N_IMG * BATCH * C * 196 * es
+        fwd = lambda: ops.roi_align_forward(feats, rois, (14, 14), 1 / 16, 0, True, True)
+        bwd = lambda: ops.roi_align_backward(wl.grad_pooled, rois, feats.shape, 1 / 16, 0, True, True)
+        for _ in range(3):
+            fwd()
+            bwd()
+        kernel_ms["roi_align_fwd"] = time_kernel(fwd, 10, flush)
+        kernel_ms["roi_align_bwd"] = time_kernel(bwd, 10, flush)
+        peak, peak_src = measured_peak_gbs()
+        dom = max(kernel_ms, key=kernel_ms.get)
+        achieved = alg_bytes / (kernel_ms[dom] * 1e-3) / 1e9
+        roofline = {
+            "kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes,
+            "per_kernel": {k: {"ms": v, "GBps": alg_bytes / (v * 1e-3) / 1e9, "frac": alg_bytes / (v * 1e-3) / 1e9 / peak}
+                           for k, v in kernel_ms.items()},
+        }
+
+    # CPU baseline on the box's host cores (rank 0, N = 1 only): the oracle port on a bounded sample
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        w, meta, x, xw, gp = cpu_workload()
+        hs = make_inputs(2000)
+        gen = _seeded(1000)
+        roi_sample = 64
+        cpu_reference_step(hs, w, meta, gen, x, xw, gp, 8)  # warm-up
+        t0 = time.perf_counter()
+        _, tl, tr, tp, _, _ = cpu_reference_step(hs, w, meta, gen, x, xw, gp, roi_sample)
+        wall = time.perf_counter() - t0
+        est = tl + tp + tr * (BATCH / roi_sample)
+        cpu_baseline = {
+            "value": N_IMG / est, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"one step: label+sample and transfer+loss+backward on the full 2x512-RoI workload, ROIAlign "
+                      f"fwd+bwd on {roi_sample} of 512 RoIs/image scaled x{BATCH // roi_sample} "
+                      f"(measured {wall:.1f}s, estimated full step {est:.1f}s)",
+        }
+
+    if rank == 0:
+        ms_step = total_ms / args.steps
+        value = world * N_IMG / (ms_step / 1000.0)
+        e2e_value = world * N_IMG / (e2e_ms / args.steps / 1000.0)
+        line = {
+            "metric": "RoI-stage images/sec (VOC R101-C4 FT train step)", "value": value, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic", "config": workload_config(args.dtype),
+            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": wl.h2d_bytes(), "d2h_bytes_per_step": 4 + 4 * N_IMG * 2},
+            "gpu_launches": int(launches),
+            "gpu_launches_note": "kernels of libunit_b200.so launched in the timed region (cuBLAS GEMMs and ATen "
+                                 "loss kernels not counted)",
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--dtype", choices=["f32", "bf16"], default="f32")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

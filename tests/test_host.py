@@ -1,0 +1,142 @@
+"""CPU: host-side logic (config, registries, containers) and the C-ABI surface (symbols only, no compute)."""
+import ctypes
+import glob
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+REF_CFG = "/root/reference/configs"
+
+
+def test_config_yacs_semantics(tmp_path):
+    from unit_b200.config import CfgNode, get_cfg, load_cfg
+
+    cfg = load_cfg(os.path.join(ROOT, "configs", "voc_split1_ft.yaml"), ["MODEL.ROI_HEADS.SCORE_THRESH_TEST", "0.01",
+                                                                         "INPUT.MIN_SIZE_TRAIN", "(640, 800)"])
+    assert cfg.MODEL.ROI_HEADS.NAME == "WSROIHeadFineTune"            # own value
+    assert cfg.MODEL.ROI_BOX_HEAD.POOLER_TYPE == "ROIAlignV2"          # inherited through _BASE_
+    assert cfg.MODEL.ROI_HEADS.SCORE_THRESH_TEST == 0.01 and cfg.INPUT.MIN_SIZE_TRAIN == (640, 800)
+    assert cfg.MODEL.ROI_HEADS.FINETUNE_TERMS.CLASSIFIER == ["lingual", "visual"]
+    with pytest.raises(KeyError):
+        cfg.merge_from_list(["MODEL.NOT_A_KEY", 1])
+    with pytest.raises(ValueError):
+        cfg.merge_from_list(["MODEL.ROI_HEADS.NUM_CLASSES", "twenty"])
+    bad = tmp_path / "bad.yaml"
+    bad.write_text("MODEL:\n  UNKNOWN_SECTION: {A: 1}\n")
+    with pytest.raises(KeyError):
+        load_cfg(str(bad))
+    c2 = cfg.clone()
+    c2.MODEL.ROI_HEADS.NUM_CLASSES = 3
+    assert cfg.MODEL.ROI_HEADS.NUM_CLASSES == 20
+    cfg.freeze()
+    with pytest.raises(AttributeError):
+        cfg.MODEL.MASK_ON = True
+    assert isinstance(get_cfg().MODEL, CfgNode)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG), reason="reference checkout not present")
+def test_reference_yamls_load_unchanged():
+    from unit_b200.config import load_cfg
+
+    files = [f for f in glob.glob(REF_CFG + "/**/*.yaml", recursive=True) if not f.endswith("Base-RCNN-C4.yaml")]
+    assert len(files) == 24
+    for f in files:
+        cfg = load_cfg(f)
+        assert cfg.MODEL.ROI_HEADS.NAME.startswith("WSROIHead")
+        assert cfg.MODEL.ROI_HEADS.FAST_RCNN.NAME.startswith("SupervisedDetectorOutputs")
+
+
+def test_registries_hold_reference_names():
+    from unit_b200 import d2compat  # noqa: F401
+    from unit_b200.registry import (FAST_RCNN_REGISTRY, ROI_BOX_HEAD_REGISTRY, ROI_HEADS_REGISTRY,
+                                    ROI_MASK_HEAD_REGISTRY, WEAK_DETECTOR_FAST_RCNN_REGISTRY)
+
+    for n in ("WSROIHeadNoMeta", "WSROIHeadFineTune", "WSROIHeadNoMetaWithMask", "WSROIHeadWithMaskFineTune",
+              "WeakDetectorHead"):
+        assert n in ROI_HEADS_REGISTRY
+    for n in ("SupervisedDetectorOutputsBase", "SupervisedDetectorOutputsFineTune",
+              "SupervisedDetectorOutputsWeakFineTune", "WeakDetectorOutputsBaseWrapper"):
+        assert n in FAST_RCNN_REGISTRY
+    assert "WeakDetectorOutputsBase" in WEAK_DETECTOR_FAST_RCNN_REGISTRY
+    assert "Res5BoxHead" in ROI_BOX_HEAD_REGISTRY and "Res5BoxHeadWithMask" in ROI_BOX_HEAD_REGISTRY
+    assert "MaskRCNNConvUpsampleHeadWithFineTune" in ROI_MASK_HEAD_REGISTRY
+
+
+def test_heads_build_with_reference_state_dict_keys():
+    from unit_b200.config import load_cfg
+    from unit_b200.roi_heads import build_roi_heads
+    from unit_b200.structures import ShapeSpec
+
+    cfg = load_cfg(os.path.join(ROOT, "configs", "voc_split1_ft.yaml"),
+                   ["MODEL.ROI_HEADS.EMBEDDING_PATH", os.path.join(ROOT, "tests", "golden", "glove_mean.pt")])
+    head = build_roi_heads(cfg, {"res4": ShapeSpec(channels=1024, stride=16)})
+    keys = set(head.state_dict().keys())
+    for k in ("box_predictor.cls_score_delta.weight", "box_predictor.bbox_pred_delta.bias",
+              "box_predictor.cls_score_ft.weight", "box_predictor.bbox_pred_ft.bias",
+              "box_predictor.weak_detector_head.oicr_predictors.2.weight",
+              "box_predictor.weak_detector_head.classifier_stream.weight", "box_predictor.embeddings.weight",
+              "box_head.res5.0.conv1.weight", "box_head.res5.0.shortcut.norm.running_var",
+              "weak_box_head.res5.2.conv3.weight"):
+        assert k in keys, k
+    trainable = sorted(n for n, p in head.named_parameters() if p.requires_grad)
+    assert trainable == ["box_predictor.bbox_pred_ft.bias", "box_predictor.bbox_pred_ft.weight",
+                         "box_predictor.cls_score_ft.bias", "box_predictor.cls_score_ft.weight"]
+    assert head._coco_indexer_tensor.tolist() == [4, 1, 14, 8, 39, 5, 2, 15, 56, 19, 60, 16, 17, 3, 0, 58, 18, 57, 6, 62]
+    assert head.box_pooler.aligned and head.box_pooler.output_size == (14, 14) and head.box_pooler.scales == (1 / 16,)
+
+
+def test_containers():
+    from unit_b200.structures import Boxes, Instances
+
+    b = Boxes(torch.tensor([[0.0, 0.0, 10.0, 20.0], [5.0, 5.0, 4.0, 30.0]]))
+    assert b.area().tolist() == [200.0, -25.0] and b.nonempty().tolist() == [True, False]
+    b.clip((15, 8))
+    assert b.tensor.tolist() == [[0.0, 0.0, 8.0, 15.0], [5.0, 5.0, 4.0, 15.0]]
+    i = Instances((15, 8), proposal_boxes=b, objectness_logits=torch.tensor([1.0, 2.0]))
+    assert len(i) == 2 and len(i[torch.tensor([True, False])]) == 1
+    with pytest.raises(ValueError):
+        i.scores = torch.zeros(3)
+    c = Instances.cat([i, i])
+    assert len(c) == 4 and isinstance(c.proposal_boxes, Boxes)
+    assert Boxes(torch.empty(0)).tensor.shape == (0, 4)
+
+
+def test_no_cpu_fallback():
+    from unit_b200 import ops
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.pairwise_iou(torch.zeros(1, 4), torch.zeros(1, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.roi_align(torch.zeros(1, 8, 4, 4), torch.zeros(1, 5), 14)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads and exports exactly the entry points include/unit_b200.h declares."""
+    from unit_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "unit_b200.h")).read()
+    declared = set(re.findall(r"\b(unit_[a-z0-9_]+)\s*\(", header))
+    declared.discard("unit_stream_t")
+    assert len(declared) >= 20
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as ge
+
+        ge.build()
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(handle, name), f"{name} declared in include/unit_b200.h but not exported"
+    assert set(_lib.exported_symbols()) <= declared
+    lib = _lib.lib()
+    assert lib.unit_version() >= 100
+    assert lib.unit_roi_align_workspace_bytes(4) >= 16
+    assert lib.unit_nms_workspace_bytes(2, 1000) > 36 * 2000
+
+
+def test_product_never_imports_oracle():
+    for f in glob.glob(os.path.join(ROOT, "unit_b200", "*.py")):
+        src = open(f).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f

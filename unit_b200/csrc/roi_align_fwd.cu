@@ -93,40 +93,54 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Build the tables of one RoI with the whole warp.
+//   x entry s: (hx * inv_count | LASTCOL sign, lx * inv_count | END sign); LASTCOL = last sample whose lower tap is
+//   this column, END = last sample of its bin.  Samples clamped to the last column (x >= W-1, value F[W-1]) are
+//   re-expressed as lo = W-2 with weights (0, 1): identical value, and the window never has to step past W-1.
 template <typename T>
 __device__ __forceinline__ void build_tables(const float* __restrict__ roi, const Params& p, WarpArea<T>* wa,
                                              int lane) {
   const Geom g = roi_geom(roi, p.scale, P, P, p.sampling_ratio, p.aligned);
   int mode = 1;
   if (g.gw <= 0 || g.gh <= 0) mode = 0;
-  else if (g.gw > MAXG || g.gh > MAXG) mode = 2;
+  else if (g.gw > MAXG || g.gh > MAXG || p.W < 2) mode = 2;
   bool jump = false;
   if (mode == 1) {
     const int ns = P * g.gw;
-    for (int s = lane; s < ns; s += 32) {
-      int lo, hi, plo, phi;
-      float l, h, pl, phh;
-      axis_tap(sample_coord(g.start_w, g.bin_w, s / g.gw, s % g.gw, g.gw), p.W, lo, hi, l, h);
-      int adv = 0;
-      if (s > 0) {
-        axis_tap(sample_coord(g.start_w, g.bin_w, (s - 1) / g.gw, (s - 1) % g.gw, g.gw), p.W, plo, phi, pl, phh);
-        adv = lo - plo;
-      } else {
-        wa->hdr.x0 = lo;
+    const float inv = 1.f / g.count;
+    const float inv_gw = 1.f / (float)g.gw;
+    // 31 samples per round; lane 31 evaluates the look-ahead sample of the next round's lane 0
+    for (int s0 = 0; s0 < ns; s0 += 31) {
+      const int s = s0 + lane;
+      int lo = 0x7fffffff, hi;
+      float l = 0.f, h = 0.f;
+      if (s < ns) {
+        const int pw = (int)(((float)s + 0.5f) * inv_gw);  // s / gw (exact for s < 2^20)
+        axis_tap(sample_coord(g.start_w, g.bin_w, pw, s - pw * g.gw, g.gw), p.W, lo, hi, l, h);
+        if (lo >= p.W - 1) {  // clamped sample: 0 * F[W-2] + 1 * F[W-1]  (or 0 * .. + 0 * .. when invalid)
+          lo = p.W - 2;
+          l = h;  // valid: h == 1, l == 0 -> (0, 1); invalid: (0, 0)
+          h = 0.f;
+        }
       }
-      jump |= (adv > 1 || adv < 0);
-      const bool end = (s % g.gw) == g.gw - 1;
-      float2 e;
-      e.x = adv ? -h : h;  // -0.0f keeps the flag when the weight is zero
-      e.y = end ? -l : l;
-      if (adv && h == 0.f) e.x = __uint_as_float(0x80000000u);
-      if (end && l == 0.f) e.y = __uint_as_float(0x80000000u);
-      wa->xtab[s] = e;
+      const int nlo = __shfl_down_sync(0xffffffffu, lo, 1);
+      if (s < ns && lane < 31) {
+        const bool last = (s == ns - 1) || (nlo != lo);
+        jump |= (s < ns - 1) && (nlo - lo > 1 || nlo < lo);
+        const int pw = (int)(((float)s + 0.5f) * inv_gw);
+        const bool end = (s - pw * g.gw) == g.gw - 1;
+        float2 e;
+        e.x = __uint_as_float(__float_as_uint(h * inv) | (last ? 0x80000000u : 0u));
+        e.y = __uint_as_float(__float_as_uint(l * inv) | (end ? 0x80000000u : 0u));
+        wa->xtab[s] = e;
+        if (s == 0) wa->hdr.x0 = lo;
+      }
     }
     if (lane < 2) wa->xtab[ns + lane] = make_float2(0.f, 0.f);
+    const float inv_gh = 1.f / (float)g.gh;
     for (int s = lane; s < P * g.gh; s += 32) {
       YTap t;
-      axis_tap(sample_coord(g.start_h, g.bin_h, s / g.gh, s % g.gh, g.gh), p.H, t.lo, t.hi, t.l, t.h);
+      const int ph = (int)(((float)s + 0.5f) * inv_gh);
+      axis_tap(sample_coord(g.start_h, g.bin_h, ph, s - ph * g.gh, g.gh), p.H, t.lo, t.hi, t.l, t.h);
       t.lo *= p.W;
       t.hi *= p.W;
       wa->ytab[s] = t;
@@ -149,89 +163,124 @@ __device__ __forceinline__ void build_tables(const float* __restrict__ roi, cons
 
 template <int GH>
 struct Taps {
-  YTap a[GH > 0 ? GH : 1], b[GH > 0 ? GH : 1];
+  const float2* alo[GH > 0 ? GH : 1];
+  const float2* ahi[GH > 0 ? GH : 1];
+  const float2* blo[GH > 0 ? GH : 1];
+  const float2* bhi[GH > 0 ? GH : 1];
+  float ah[GH > 0 ? GH : 1], al[GH > 0 ? GH : 1], bh[GH > 0 ? GH : 1], bl[GH > 0 ? GH : 1];
 };
 
-// vertically interpolated float2 (channel pair) of column `col` for rows a and b
+// vertically interpolated float2 (channel pair) of the column `off` elements past the tap pointers, rows a and b
 template <int GH>
-__device__ __forceinline__ void column(const float2* __restrict__ pl, const Taps<GH>& t, const YTap* ya, const YTap* yb,
-                                       int gh, int col, float2& va, float2& vb) {
+__device__ __forceinline__ void column(const Taps<GH>& t, const float2* __restrict__ pl, const YTap* ya,
+                                       const YTap* yb, int gh, int col, int off, float2& va, float2& vb) {
   va = make_float2(0.f, 0.f);
   vb = make_float2(0.f, 0.f);
   if (GH > 0) {
 #pragma unroll
     for (int i = 0; i < GH; ++i) {
-      va = ffma2(t.a[i].h, pl[t.a[i].lo + col], va);
-      va = ffma2(t.a[i].l, pl[t.a[i].hi + col], va);
-      vb = ffma2(t.b[i].h, pl[t.b[i].lo + col], vb);
-      vb = ffma2(t.b[i].l, pl[t.b[i].hi + col], vb);
+      va = ffma2(t.ah[i], t.alo[i][off], va);
+      va = ffma2(t.al[i], t.ahi[i][off], va);
+      vb = ffma2(t.bh[i], t.blo[i][off], vb);
+      vb = ffma2(t.bl[i], t.bhi[i][off], vb);
     }
   } else {
     for (int i = 0; i < gh; ++i) {
       const YTap a = ya[i], b = yb[i];
-      va = ffma2(a.h, pl[a.lo + col], va);
-      va = ffma2(a.l, pl[a.hi + col], va);
-      vb = ffma2(b.h, pl[b.lo + col], vb);
-      vb = ffma2(b.l, pl[b.hi + col], vb);
+      va = ffma2(a.h, pl[a.lo + col + off], va);
+      va = ffma2(a.l, pl[a.hi + col + off], va);
+      vb = ffma2(b.h, pl[b.lo + col + off], vb);
+      vb = ffma2(b.l, pl[b.hi + col + off], vb);
     }
   }
 }
 
+// Lane task: rows {q, q+7} of channels {2cp, 2cp+1}.  The window (lo, hi, next) rotates through three register
+// sets by unrolling the column loop three times, so advancing costs no register moves; the inner loop consumes the
+// samples whose lower tap is the current column.
 template <typename T, int GH>
 __device__ __forceinline__ void task(const float2* __restrict__ pl, int W, const WarpArea<T>* wa, int q, int cp,
                                      T* __restrict__ stage) {
   const int gh = wa->hdr.gh;
   const YTap* ya = wa->ytab + q * gh;
   const YTap* yb = wa->ytab + (q + 7) * gh;
+  int col = wa->hdr.x0;
   Taps<GH> t;
   if (GH > 0) {
 #pragma unroll
     for (int i = 0; i < GH; ++i) {
-      t.a[i] = ya[i];
-      t.b[i] = yb[i];
+      const YTap a = ya[i], b = yb[i];
+      t.alo[i] = pl + a.lo + col;
+      t.ahi[i] = pl + a.hi + col;
+      t.blo[i] = pl + b.lo + col;
+      t.bhi[i] = pl + b.hi + col;
+      t.ah[i] = a.h;
+      t.al[i] = a.l;
+      t.bh[i] = b.h;
+      t.bl[i] = b.l;
     }
   }
-  const int wm1 = W - 1;
-  int cur = wa->hdr.x0;
-  float2 lo_a, lo_b, hi_a, hi_b, nx_a, nx_b;
-  column<GH>(pl, t, ya, yb, gh, cur, lo_a, lo_b);
-  column<GH>(pl, t, ya, yb, gh, min(cur + 1, wm1), hi_a, hi_b);
-  column<GH>(pl, t, ya, yb, gh, min(cur + 2, wm1), nx_a, nx_b);
-  const float inv = wa->hdr.inv_count;
-  const int ns = wa->hdr.nsamp;
+  float2 w0a, w0b, w1a, w1b, w2a, w2b;
+  column<GH>(t, pl, ya, yb, gh, col, 0, w0a, w0b);
+  column<GH>(t, pl, ya, yb, gh, col, 1, w1a, w1b);
+  column<GH>(t, pl, ya, yb, gh, col, 2, w2a, w2b);
+  int remaining = wa->hdr.nsamp;
   float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);
-  T* da0 = stage + (2 * cp) * (P * P) + q * P;  // row q of channel 2cp; channel 2cp+1 is P*P further
-  T* db0 = da0 + 7 * P;                         // row q+7
-  float2 e = wa->xtab[0];
-  for (int s = 0; s < ns; ++s) {
-    const float2 en = wa->xtab[s + 1];
-    const bool adv = __float_as_uint(e.x) >> 31;
-    const bool end = __float_as_uint(e.y) >> 31;
-    const float hx = fabsf(e.x), lx = fabsf(e.y);
-    if (adv) {
-      ++cur;
-      lo_a = hi_a;
-      lo_b = hi_b;
-      hi_a = nx_a;
-      hi_b = nx_b;
-      column<GH>(pl, t, ya, yb, gh, min(cur + 2, wm1), nx_a, nx_b);
-    }
-    acc_a = ffma2(hx, lo_a, acc_a);
-    acc_b = ffma2(hx, lo_b, acc_b);
-    acc_a = ffma2(lx, hi_a, acc_a);
-    acc_b = ffma2(lx, hi_b, acc_b);
-    if (end) {
-      stf(da0, acc_a.x * inv);
-      stf(da0 + P * P, acc_a.y * inv);
-      stf(db0, acc_b.x * inv);
-      stf(db0 + P * P, acc_b.y * inv);
-      ++da0;
-      ++db0;
-      acc_a = make_float2(0.f, 0.f);
-      acc_b = make_float2(0.f, 0.f);
-    }
-    e = en;
+  T* da = stage + (2 * cp) * (P * P) + q * P;  // row q of channel 2cp; channel 2cp+1 is P*P further
+  T* db = da + 7 * P;                          // row q+7
+  const float2* xt = wa->xtab;
+  float2 e = xt[0];
+
+#define UNIT_CONSUME(LA, LB, HA, HB)                              \
+  {                                                               \
+    bool lastcol;                                                 \
+    do {                                                          \
+      const float2 en = xt[1];                                    \
+      ++xt;                                                       \
+      lastcol = (__float_as_uint(e.x) >> 31) != 0;                \
+      const bool end = (__float_as_uint(e.y) >> 31) != 0;         \
+      const float hx = fabsf(e.x), lx = fabsf(e.y);               \
+      acc_a = ffma2(hx, LA, acc_a);                               \
+      acc_b = ffma2(hx, LB, acc_b);                               \
+      acc_a = ffma2(lx, HA, acc_a);                               \
+      acc_b = ffma2(lx, HB, acc_b);                               \
+      if (end) {                                                  \
+        stf(da, acc_a.x);                                         \
+        stf(da + P * P, acc_a.y);                                 \
+        stf(db, acc_b.x);                                         \
+        stf(db + P * P, acc_b.y);                                 \
+        ++da;                                                     \
+        ++db;                                                     \
+        acc_a = make_float2(0.f, 0.f);                            \
+        acc_b = make_float2(0.f, 0.f);                            \
+      }                                                           \
+      e = en;                                                     \
+      --remaining;                                                \
+    } while (!lastcol);                                           \
   }
+
+  while (true) {
+    UNIT_CONSUME(w0a, w0b, w1a, w1b);
+    if (remaining <= 0) break;
+    column<GH>(t, pl, ya, yb, gh, col, 3, w0a, w0b);
+    UNIT_CONSUME(w1a, w1b, w2a, w2b);
+    if (remaining <= 0) break;
+    column<GH>(t, pl, ya, yb, gh, col, 4, w1a, w1b);
+    UNIT_CONSUME(w2a, w2b, w0a, w0b);
+    if (remaining <= 0) break;
+    column<GH>(t, pl, ya, yb, gh, col, 5, w2a, w2b);
+    col += 3;
+    if (GH > 0) {
+#pragma unroll
+      for (int i = 0; i < GH; ++i) {
+        t.alo[i] += 3;
+        t.ahi[i] += 3;
+        t.blo[i] += 3;
+        t.bhi[i] += 3;
+      }
+    }
+  }
+#undef UNIT_CONSUME
 }
 
 // direct evaluation (grid larger than MAXG or irregular sample steps): every lane fills its rows sample by sample
@@ -392,7 +441,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) roi_align_fwd_slab2(const Params 
 }
 
 static int pair_stride_host(int HW) {
-  int s = HW;
+  int s = HW + 3;  // the window reads up to 3 elements past a row end (never used; see build_tables)
   while ((s & 15) != 1) ++s;
   return s;
 }
