@@ -65,7 +65,9 @@ def make_inputs(seed, dtype=torch.float32):
         gt = _boxes(n_gt, IMG_HW[0], IMG_HW[1], g, 32.0)
         pb = _boxes(P_RPN, IMG_HW[0], IMG_HW[1], g, 16.0)
         k = P_RPN // 4  # 25 % of the proposals are GT boxes jittered by <= 10 % so that positives exist
-        pb[:k] = gt[torch.randint(0, n_gt, (k,), generator=g)] * (1 + 0.1 * (torch.rand(k, 4, generator=g) - 0.5))
+        src = gt[torch.randint(0, n_gt, (k,), generator=g)]
+        wh = torch.cat([src[:, 2:] - src[:, :2]] * 2, 1)
+        pb[:k] = src + 0.2 * (torch.rand(k, 4, generator=g) - 0.5) * wh
         pb[:, 0::2] = pb[:, 0::2].clamp(0, IMG_HW[1])
         pb[:, 1::2] = pb[:, 1::2].clamp(0, IMG_HW[0])
         props.append(pb)
@@ -259,7 +261,7 @@ def cpu_reference_step(host_set, weights, head_meta, gen, x, xw, grad_pooled, ro
     loss = loss_cls + (bbox[fg[:, None], cols] - tgt).abs().sum() / gt_classes.numel()
     loss.backward()
     t_pred = time.perf_counter() - t0
-    return float(loss), t_label, t_roi, t_pred, pooled, gfeat
+    return float(loss.detach()), t_label, t_roi, t_pred, pooled, gfeat
 
 
 def cpu_workload(rank=0):

@@ -93,14 +93,11 @@ class Res5BoxHead(nn.Module):
 
 @ROI_BOX_HEAD_REGISTRY.register()
 class Res5BoxHeadWithMask(Res5BoxHead):
-    """box_head.py:137-141: keeps the 7x7 map (the heads mean-pool it for the box branch)."""
+    """box_head.py:137-141: keeps the 7x7 map (the heads mean-pool it for the box branch); ``output_shape`` is
+    inherited, i.e. still (2048, 1, 1), which is what sizes the predictor and the mask head in the reference."""
 
     def forward(self, x):
         return self.res5(x)
-
-    @property
-    def output_shape(self):
-        return ShapeSpec(channels=self.out_channels, height=7, width=7)
 
 
 class _MaskHeadBase(nn.Module):
