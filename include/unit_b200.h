@@ -114,6 +114,15 @@ int unit_softmax_decode(const float* scores, const float* deltas, const float* p
 int unit_box_get_deltas(const float* src, const float* tgt, float* deltas, int R, float wx, float wy, float ww,
                         float wh, unit_stream_t stream);
 
+/* Fused Fast R-CNN loss + gradients.  Replaces [D2] FastRCNNOutputs.losses as called at fast_rcnn.py:438-445:
+ * loss_cls = mean softmax cross-entropy over the R sampled RoIs; loss_box_reg = sum over foreground RoIs of
+ * smooth_l1(pred_deltas[gt class] - get_deltas(proposal, gt_box)) / R.  losses [2] = (loss_cls, loss_box_reg);
+ * d_scores [R,K+1], d_deltas [R,4K] = their gradients (for upstream gradient 1).  workspace: 2*R floats. */
+int unit_fastrcnn_loss(const float* scores, const float* deltas, const float* proposals, const float* gt_boxes,
+                       const int64_t* gt_classes, int R, int K, float wx, float wy, float ww, float wh,
+                       float smooth_l1_beta, float* losses, float* d_scores, float* d_deltas, void* workspace,
+                       size_t workspace_bytes, unit_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * fast_rcnn_inference for a batch of images in two launches.  Replaces [D2] fast_rcnn_inference(_single_image)
  * (fast_rcnn.py:461-468, weak_detector_fast_rcnn.py:299-306, meta_arch/rcnn.py:526): drop non-finite rows, drop

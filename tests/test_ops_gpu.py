@@ -460,3 +460,32 @@ def test_mask_paste_full_size(ops):
     got = ops.mask_paste(masks.cuda(), boxes.cuda(), (H, W), 0.5).cpu()
     mism = (got != want).sum().item()
     assert mism <= 1e-5 * want.numel(), f"{mism} mismatching pixels of {want.numel()}"
+
+
+def test_fused_fastrcnn_loss_and_grads(ops):
+    """[D2] FastRCNNOutputs.losses (CE mean + smooth-L1 on get_deltas / R) and its autograd, fused in one kernel."""
+    import torch.nn.functional as F
+    from oracle.d2.ops import Box2BoxTransform, smooth_l1_loss
+
+    g = seeded(97)
+    for K, beta in ((20, 0.0), (80, 0.5)):
+        R = 333
+        scores = (torch.randn(R, K + 1, generator=g) * 2).requires_grad_(True)
+        deltas = torch.randn(R, 4 * K, generator=g).requires_grad_(True)
+        props = random_boxes(R, 800, 1333, g, 16.0)
+        gts = random_boxes(R, 800, 1333, g, 24.0)
+        cls = torch.randint(0, K + 1, (R,), generator=g)
+        loss_cls = F.cross_entropy(scores, cls)
+        fg = ((cls >= 0) & (cls < K)).nonzero().squeeze(1)
+        cols = 4 * cls[fg][:, None] + torch.arange(4)
+        tgt = Box2BoxTransform((10.0, 10.0, 5.0, 5.0)).get_deltas(props, gts)[fg]
+        loss_box = smooth_l1_loss(deltas[fg[:, None], cols], tgt, beta, reduction="sum") / R
+        (2.0 * loss_cls + 3.0 * loss_box).backward()
+        s2 = scores.detach().cuda().requires_grad_(True)
+        d2 = deltas.detach().cuda().requires_grad_(True)
+        lc, lb = ops.fastrcnn_loss(s2, d2, props.cuda(), gts.cuda(), cls.cuda(), beta=beta)
+        (2.0 * lc + 3.0 * lb).backward()
+        assert_close_rms(lc.detach().cpu(), loss_cls.detach(), 1e-5, "loss_cls")
+        assert_close_rms(lb.detach().cpu(), loss_box.detach(), 1e-5, "loss_box")
+        assert_close_rms(s2.grad.cpu(), scores.grad, 1e-5, "d scores")
+        assert_close_rms(d2.grad.cpu(), deltas.grad, 1e-5, "d deltas")

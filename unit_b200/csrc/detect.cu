@@ -640,3 +640,129 @@ int unit_batched_nms(const float* boxes, const float* scores, const int64_t* idx
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------- fused Fast R-CNN loss
+// [D2] FastRCNNOutputs.losses (reached at fast_rcnn.py:438-445): softmax cross-entropy (mean over all RoIs) +
+// smooth-L1 between the predicted deltas of the GT class and Box2BoxTransform.get_deltas(proposal, gt_box), summed
+// over foreground RoIs and divided by the number of RoIs.  One launch produces both losses AND both gradients
+// (SURVEY.md section 8f rank 2); a second single-block launch reduces the per-row terms in a fixed order.
+namespace unit {
+namespace detect {
+
+__global__ void fastrcnn_loss_kernel(const float* __restrict__ scores, const float* __restrict__ deltas,
+                                     const float4* __restrict__ proposals, const float4* __restrict__ gt_boxes,
+                                     const int64_t* __restrict__ gt_classes, int R, int K, float wx, float wy,
+                                     float ww, float wh, float beta, float* __restrict__ row_loss,
+                                     float* __restrict__ d_scores, float* __restrict__ d_deltas) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int K1 = K + 1;
+  const float invR = 1.f / (float)R;
+  const int cls = (int)gt_classes[r];
+  const float* s = scores + (long long)r * K1;
+  float m = -INFINITY;
+  for (int k = lane; k < K1; k += 32) m = fmaxf(m, s[k]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int k = lane; k < K1; k += 32) sum += expf(s[k] - m);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float lse = m + logf(sum);
+  for (int k = lane; k < K1; k += 32)
+    d_scores[(long long)r * K1 + k] = (expf(s[k] - lse) - (k == cls ? 1.f : 0.f)) * invR;
+  float box_loss = 0.f;
+  const bool fg = cls >= 0 && cls < K;
+  float dv = 0.f;
+  if (fg && lane < 4) {
+    const float4 p = proposals[r], g = gt_boxes[r];
+    const float sw = __fsub_rn(p.z, p.x), sh = __fsub_rn(p.w, p.y);
+    const float scx = __fadd_rn(p.x, __fmul_rn(0.5f, sw)), scy = __fadd_rn(p.y, __fmul_rn(0.5f, sh));
+    const float tw = __fsub_rn(g.z, g.x), th = __fsub_rn(g.w, g.y);
+    const float tcx = __fadd_rn(g.x, __fmul_rn(0.5f, tw)), tcy = __fadd_rn(g.y, __fmul_rn(0.5f, th));
+    float t;
+    if (lane == 0) t = __fdiv_rn(__fmul_rn(wx, __fsub_rn(tcx, scx)), sw);
+    else if (lane == 1) t = __fdiv_rn(__fmul_rn(wy, __fsub_rn(tcy, scy)), sh);
+    else if (lane == 2) t = __fmul_rn(ww, logf(__fdiv_rn(tw, sw)));
+    else t = __fmul_rn(wh, logf(__fdiv_rn(th, sh)));
+    const float diff = deltas[(long long)r * 4 * K + 4 * cls + lane] - t;
+    const float n = fabsf(diff);
+    if (beta < 1e-5f) {
+      box_loss = n;
+      dv = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+    } else if (n < beta) {
+      box_loss = 0.5f * n * n / beta;
+      dv = diff / beta;
+    } else {
+      box_loss = n - 0.5f * beta;
+      dv = diff > 0.f ? 1.f : -1.f;
+    }
+  }
+  for (int i = lane; i < 4 * K; i += 32) {
+    float v = 0.f;
+    const int j = i - 4 * cls;
+    if (fg && j >= 0 && j < 4) v = __shfl_sync(__activemask(), dv, j) * invR;
+    d_deltas[(long long)r * 4 * K + i] = v;
+  }
+  box_loss += __shfl_xor_sync(0xffffffffu, box_loss, 1);
+  box_loss += __shfl_xor_sync(0xffffffffu, box_loss, 2);
+  if (lane == 0) {
+    row_loss[r] = lse - s[cls >= 0 && cls < K1 ? cls : 0];
+    row_loss[R + r] = box_loss;
+  }
+}
+
+__global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int R, float* __restrict__ out) {
+  __shared__ float s0[32], s1[32];
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    a += row_loss[i];
+    b += row_loss[R + i];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s0[threadIdx.x >> 5] = a;
+    s1[threadIdx.x >> 5] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ta = 0.f, tb = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      ta += s0[w];
+      tb += s1[w];
+    }
+    out[0] = ta / (float)R;
+    out[1] = tb / (float)R;
+  }
+}
+
+}  // namespace detect
+}  // namespace unit
+
+extern "C" int unit_fastrcnn_loss(const float* scores, const float* deltas, const float* proposals,
+                                  const float* gt_boxes, const int64_t* gt_classes, int R, int K, float wx, float wy,
+                                  float ww, float wh, float smooth_l1_beta, float* losses, float* d_scores,
+                                  float* d_deltas, void* workspace, size_t workspace_bytes, unit_stream_t stream) {
+  UNIT_REQUIRE(R >= 0 && K > 0, "fastrcnn_loss: bad shape");
+  UNIT_REQUIRE(losses, "fastrcnn_loss: null losses");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (R == 0) {
+    UNIT_CUDA(cudaMemsetAsync(losses, 0, 2 * sizeof(float), st));
+    return UNIT_OK;
+  }
+  UNIT_REQUIRE(scores && deltas && proposals && gt_boxes && gt_classes && d_scores && d_deltas,
+               "fastrcnn_loss: null pointer");
+  UNIT_REQUIRE((((uintptr_t)proposals | (uintptr_t)gt_boxes) & 15) == 0, "fastrcnn_loss: boxes must be 16-byte aligned");
+  if (!workspace || workspace_bytes < (size_t)2 * R * sizeof(float)) {
+    set_error("fastrcnn_loss: workspace too small");
+    return UNIT_EWORKSPACE;
+  }
+  unit::detect::fastrcnn_loss_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(
+      scores, deltas, (const float4*)proposals, (const float4*)gt_boxes, gt_classes, R, K, wx, wy, ww, wh,
+      smooth_l1_beta, (float*)workspace, d_scores, d_deltas);
+  UNIT_CHECK_LAUNCH("fastrcnn_loss_kernel");
+  unit::detect::loss_reduce_kernel<<<1, 1024, 0, st>>>((const float*)workspace, R, losses);
+  UNIT_CHECK_LAUNCH("loss_reduce_kernel");
+  return UNIT_OK;
+}

@@ -1,31 +1,55 @@
-// ROIAlign backward, slab-resident kernel v2.
+// ROIAlign backward, slab-resident kernel.
 //
-// Transpose of roi_align_fwd.cu with the same decomposition: a persistent CTA keeps the GRADIENT tile of one
-// (image, 8-channel slab) -- channel-pair interleaved float2, 134 KB for the 50x84 map -- in shared memory; each of
-// its 12 warps pulls RoIs of that slab, streams the RoI's [8][14][14] grad_out block in with one TMA bulk load
-// (cp.async.bulk.shared::cta.global + mbarrier, overlapped with the table build), and lane (q, cp) scatters rows
-// {q, q+7} of channels {2cp, 2cp+1}: horizontal spread in registers over a two-column window, vertical spread with
-// one 64-bit shared-memory CAS-add per tap (both channels at once).  The tile goes to HBM once per segment:
-// torchvision issues gh*gw*4 global atomics per output element (~1e9 for 2x512 RoIs), this kernel issues none in the
-// steady state (only the per-segment tile merge uses red.global).
+// Same decomposition as roi_align_fwd.cu, transposed.  A persistent CTA keeps the GRADIENT tile of one
+// (image, 8-channel slab) -- channel-pair interleaved float2, 134 KB for the 50x84 map -- in shared memory.  Each of
+// its warps pulls RoIs of that slab, streams the RoI's [8][14][14] grad_out block in with one TMA bulk load
+// (cp.async.bulk.shared::cta.global + mbarrier, overlapped with the table build; the following RoI's block is
+// prefetched into L2), and scatters it column-wise: lane (c, cp) OWNS feature column x0 + c of channel pair cp for
+// this RoI.  For each of the 14 bin rows it gathers the horizontally spread value u = sum_s w_s * g[row][bin(s)] over
+// the samples touching its column (two contiguous sample ranges of the x-table), then spreads u vertically through a
+// two-row register window, so that every tile cell (y, x) of the RoI's footprint receives exactly ONE 64-bit
+// shared-memory CAS-add (both channels at once).  Lanes of a warp never collide (distinct columns / planes); only
+// different warps (different RoIs) can, and rarely.  Per RoI that is footprint-many atomics on shared memory instead
+// of torchvision's 4*gh*gw global atomics per output element (~1e9 for 2x512 RoIs).
+// The tile reaches HBM once per segment (plain stores when the CTA owns the whole (image, slab), red.global else).
 #include "roi_slab.cuh"
 
 namespace unit {
 namespace roi {
 namespace v2 {
 
+constexpr int BMAXG = 4;             // sampling grid handled with tables in the backward (RoI side <= 56 px)
+constexpr int BMAXS = P * BMAXG;
+constexpr int BNWARPS = 12;
+constexpr int BNTHREADS = BNWARPS * 32;
+
+struct __align__(16) XSamp {
+  float h, l;  // weights of column lo and lo+1, already scaled by 1/count
+  int pw;      // bin column of the sample
+  int pad;
+};
+
+template <typename T>
+struct __align__(16) BwdArea {
+  int gw, gh, mode, x0, y0, ncols, nsx, nsy;
+  float inv_count, start_w, start_h, bin_w, bin_h;
+  int pad[3];
+  XSamp xs[BMAXS];
+  int colstart[BMAXS + 4];   // colstart[c] = first sample whose lower tap is >= x0 + c   (ncols + 1 entries)
+  float2 ys[BMAXS + 2];      // (hy | LASTROW sign, ly)
+  __align__(16) T stage[CS * P * P];
+  uint64_t bar;
+  uint64_t pad2;
+};
+
 __device__ __forceinline__ void smem_add2(float2* addr, float2 v) {
   unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
   unsigned long long old = *a, assumed;
   do {
     assumed = old;
-    float2 cur;
-    cur.x = __uint_as_float((unsigned)(assumed & 0xffffffffull));
-    cur.y = __uint_as_float((unsigned)(assumed >> 32));
-    cur.x += v.x;
-    cur.y += v.y;
-    const unsigned long long nv =
-        ((unsigned long long)__float_as_uint(cur.y) << 32) | (unsigned long long)__float_as_uint(cur.x);
+    const float x = __uint_as_float((unsigned)(assumed & 0xffffffffull)) + v.x;
+    const float y = __uint_as_float((unsigned)(assumed >> 32)) + v.y;
+    const unsigned long long nv = ((unsigned long long)__float_as_uint(y) << 32) | (unsigned long long)__float_as_uint(x);
     old = atomicCAS(a, assumed, nv);
   } while (old != assumed);
 }
@@ -57,122 +81,166 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t
                "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
                : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 
-template <int GH>
-struct BTaps {
-  float2* alo[GH > 0 ? GH : 1];
-  float2* ahi[GH > 0 ? GH : 1];
-  float2* blo[GH > 0 ? GH : 1];
-  float2* bhi[GH > 0 ? GH : 1];
-  float ah[GH > 0 ? GH : 1], al[GH > 0 ? GH : 1], bh[GH > 0 ? GH : 1], bl[GH > 0 ? GH : 1];
-};
-
-template <int GH>
-__device__ __forceinline__ void flush(const BTaps<GH>& t, float2* __restrict__ pl, const YTap* ya, const YTap* yb,
-                                      int gh, int col, float2 da, float2 db) {
-  const bool za = (da.x == 0.f && da.y == 0.f), zb = (db.x == 0.f && db.y == 0.f);
-  if (GH > 0) {
-#pragma unroll
-    for (int i = 0; i < GH; ++i) {
-      if (!za) {
-        smem_add2(t.alo[i] + col, make_float2(t.ah[i] * da.x, t.ah[i] * da.y));
-        if (t.al[i] != 0.f) smem_add2(t.ahi[i] + col, make_float2(t.al[i] * da.x, t.al[i] * da.y));
+// Tables of one RoI for the column-owner scatter (whole warp).
+template <typename T>
+__device__ __forceinline__ void build_bwd_tables(const float* __restrict__ roi, const Params& p, BwdArea<T>* ba,
+                                                 int lane) {
+  const Geom g = roi_geom(roi, p.scale, P, P, p.sampling_ratio, p.aligned);
+  int mode = 1;
+  if (g.gw <= 0 || g.gh <= 0) mode = 0;
+  else if (g.gw > BMAXG || g.gh > BMAXG || p.W < 2 || p.H < 2) mode = 2;
+  bool jump = false;
+  if (mode == 1) {
+    const float inv = 1.f / g.count;
+    // ---- x samples: weights, bin index, and the column -> first-sample index (colstart)
+    const int ns = P * g.gw;
+    const float inv_gw = 1.f / (float)g.gw;
+    int x0 = 0;
+    for (int s0 = 0; s0 < ns; s0 += 31) {
+      const int s = s0 + lane;
+      int lo = 0x3fffffff, hi;
+      float l = 0.f, h = 0.f;
+      int pw = 0;
+      if (s < ns) {
+        pw = (int)(((float)s + 0.5f) * inv_gw);
+        axis_tap(sample_coord(g.start_w, g.bin_w, pw, s - pw * g.gw, g.gw), p.W, lo, hi, l, h);
+        if (lo >= p.W - 1) {  // clamped / beyond: 0 * F[W-2] + (1 or 0) * F[W-1]
+          lo = p.W - 2;
+          l = h;
+          h = 0.f;
+        }
       }
-      if (!zb) {
-        smem_add2(t.blo[i] + col, make_float2(t.bh[i] * db.x, t.bh[i] * db.y));
-        if (t.bl[i] != 0.f) smem_add2(t.bhi[i] + col, make_float2(t.bl[i] * db.x, t.bl[i] * db.y));
+      if (s0 == 0) x0 = __shfl_sync(0xffffffffu, lo, 0);
+      const int nlo = __shfl_down_sync(0xffffffffu, lo, 1);
+      if (s < ns && lane < 31) {
+        XSamp e;
+        e.h = h * inv;
+        e.l = l * inv;
+        e.pw = pw;
+        e.pad = 0;
+        ba->xs[s] = e;
+        const int c = lo - x0;
+        if (c < 0 || c + 2 >= BMAXS + 4) {
+          jump = true;  // cannot happen for unit sample steps; keeps the table writes in bounds
+        } else {
+        if (s == 0) ba->colstart[0] = 0;
+        if (s < ns - 1) {
+          const int d = nlo - lo;
+          jump |= (d > 1 || d < 0);
+          if (d == 1) ba->colstart[c + 1] = s + 1;
+        } else {
+          ba->colstart[c + 1] = ns;      // end of the last lower-tap column
+          ba->colstart[c + 2] = ns;      // the column that only receives upper taps
+          ba->ncols = c + 2;
+        }
+        }
       }
     }
-  } else {
-    for (int i = 0; i < gh; ++i) {
-      const YTap a = ya[i], b = yb[i];
-      if (!za) {
-        smem_add2(pl + a.lo + col, make_float2(a.h * da.x, a.h * da.y));
-        if (a.l != 0.f) smem_add2(pl + a.hi + col, make_float2(a.l * da.x, a.l * da.y));
+    // ---- y samples: (hy | LASTROW, ly)
+    const int nsy = P * g.gh;
+    const float inv_gh = 1.f / (float)g.gh;
+    for (int s0 = 0; s0 < nsy; s0 += 31) {
+      const int s = s0 + lane;
+      int lo = 0x3fffffff, hi;
+      float l = 0.f, h = 0.f;
+      if (s < nsy) {
+        const int ph = (int)(((float)s + 0.5f) * inv_gh);
+        axis_tap(sample_coord(g.start_h, g.bin_h, ph, s - ph * g.gh, g.gh), p.H, lo, hi, l, h);
+        if (lo >= p.H - 1) {
+          lo = p.H - 2;
+          l = h;
+          h = 0.f;
+        }
       }
-      if (!zb) {
-        smem_add2(pl + b.lo + col, make_float2(b.h * db.x, b.h * db.y));
-        if (b.l != 0.f) smem_add2(pl + b.hi + col, make_float2(b.l * db.x, b.l * db.y));
+      const int nlo = __shfl_down_sync(0xffffffffu, lo, 1);
+      if (s < nsy && lane < 31) {
+        const bool last = (s == nsy - 1) || (nlo != lo);
+        if (s < nsy - 1) jump |= (nlo - lo > 1 || nlo < lo);
+        float2 e;
+        e.x = __uint_as_float(__float_as_uint(h) | (last ? 0x80000000u : 0u));
+        e.y = l;
+        ba->ys[s] = e;
+        if (s == 0) ba->y0 = lo;
       }
     }
+    if (lane == 0) {
+      ba->x0 = x0;
+      ba->nsx = ns;
+      ba->nsy = nsy;
+    }
+  }
+  if (__any_sync(0xffffffffu, jump)) mode = 2;
+  if (lane == 0) {
+    ba->gw = g.gw;
+    ba->gh = g.gh;
+    ba->inv_count = 1.f / g.count;
+    ba->mode = mode;
+    ba->start_w = g.start_w;
+    ba->start_h = g.start_h;
+    ba->bin_w = g.bin_w;
+    ba->bin_h = g.bin_h;
   }
 }
 
-template <typename T, int GH>
-__device__ __forceinline__ void bwd_task(float2* __restrict__ pl, const WarpArea<T>* wa, int q, int cp) {
-  const int gh = wa->hdr.gh;
-  const YTap* ya = wa->ytab + q * gh;
-  const YTap* yb = wa->ytab + (q + 7) * gh;
-  BTaps<GH> t;
-  if (GH > 0) {
-#pragma unroll
-    for (int i = 0; i < GH; ++i) {
-      const YTap a = ya[i], b = yb[i];
-      t.alo[i] = pl + a.lo;
-      t.ahi[i] = pl + a.hi;
-      t.blo[i] = pl + b.lo;
-      t.bhi[i] = pl + b.hi;
-      t.ah[i] = a.h;
-      t.al[i] = a.l;
-      t.bh[i] = b.h;
-      t.bl[i] = b.l;
+// lane task: feature column x0 + c of channel pair cp
+template <typename T>
+__device__ __forceinline__ void bwd_column(float2* __restrict__ tile_pair, int W, const BwdArea<T>* ba, int c, int cp) {
+  const int gh = ba->gh;
+  const int cs0 = c > 0 ? ba->colstart[c - 1] : 0;
+  const int cs1 = ba->colstart[c];
+  const int cs2 = ba->colstart[c + 1];
+  const int lo_begin = c > 0 ? cs0 : cs1;  // samples [lo_begin, cs1) contribute through their upper tap
+  const T* g0 = ba->stage + (2 * cp) * (P * P);
+  const T* g1 = g0 + P * P;
+  float2* cell = tile_pair + ba->y0 * W + ba->x0 + c;
+  float2 dlo = make_float2(0.f, 0.f), dhi = dlo;
+  const float2* ys = ba->ys;
+  for (int ph = 0; ph < P; ++ph) {
+    float2 u = make_float2(0.f, 0.f);
+    const T* r0 = g0 + ph * P;
+    const T* r1 = g1 + ph * P;
+    for (int s = lo_begin; s < cs1; ++s) {
+      const XSamp e = ba->xs[s];
+      u = ffma2(e.l, make_float2(ldf(r0 + e.pw), ldf(r1 + e.pw)), u);
+    }
+    for (int s = cs1; s < cs2; ++s) {
+      const XSamp e = ba->xs[s];
+      u = ffma2(e.h, make_float2(ldf(r0 + e.pw), ldf(r1 + e.pw)), u);
+    }
+    for (int iy = 0; iy < gh; ++iy) {
+      const float2 t = *ys++;
+      dlo = ffma2(fabsf(t.x), u, dlo);
+      dhi = ffma2(t.y, u, dhi);
+      if (__float_as_uint(t.x) >> 31) {
+        if (dlo.x != 0.f || dlo.y != 0.f) smem_add2(cell, dlo);
+        cell += W;
+        dlo = dhi;
+        dhi = make_float2(0.f, 0.f);
+      }
     }
   }
-  int col = wa->hdr.x0;
-  int remaining = wa->hdr.nsamp;
-  const T* ga = wa->stage + (2 * cp) * (P * P) + q * P;  // grad_out row q, channel 2cp (2cp+1 is P*P further)
-  const T* gb = ga + 7 * P;
-  float2 g_a = make_float2(ldf(ga), ldf(ga + P * P)), g_b = make_float2(ldf(gb), ldf(gb + P * P));
-  float2 dlo_a = make_float2(0.f, 0.f), dlo_b = dlo_a, dhi_a = dlo_a, dhi_b = dlo_a;
-  const float2* xt = wa->xtab;
-  float2 e = xt[0];
-  while (remaining > 0) {
-    const float2 en = xt[1];
-    ++xt;
-    const bool lastcol = (__float_as_uint(e.x) >> 31) != 0;
-    const bool end = (__float_as_uint(e.y) >> 31) != 0;
-    const float hx = fabsf(e.x), lx = fabsf(e.y);  // already scaled by 1/count
-    dlo_a = ffma2(hx, g_a, dlo_a);
-    dlo_b = ffma2(hx, g_b, dlo_b);
-    dhi_a = ffma2(lx, g_a, dhi_a);
-    dhi_b = ffma2(lx, g_b, dhi_b);
-    --remaining;
-    if (end && remaining > 0) {
-      ++ga;
-      ++gb;
-      g_a = make_float2(ldf(ga), ldf(ga + P * P));
-      g_b = make_float2(ldf(gb), ldf(gb + P * P));
-    }
-    if (lastcol) {
-      flush<GH>(t, pl, ya, yb, gh, col, dlo_a, dlo_b);
-      ++col;
-      dlo_a = dhi_a;
-      dlo_b = dhi_b;
-      dhi_a = make_float2(0.f, 0.f);
-      dhi_b = make_float2(0.f, 0.f);
-    }
-    e = en;
-  }
-  // the upper tap of the last column (col == last lo + 1 <= W-1)
-  flush<GH>(t, pl, ya, yb, gh, col, dlo_a, dlo_b);
+  if (dlo.x != 0.f || dlo.y != 0.f) smem_add2(cell, dlo);  // the row that only receives upper taps
 }
 
 template <typename T>
-__device__ __noinline__ void bwd_task_direct(float2* __restrict__ pl, int H, int W, const Header& hdr, int q, int cp,
-                                             const T* __restrict__ stage) {
+__device__ __noinline__ void bwd_direct(float2* __restrict__ pl, int H, int W, const BwdArea<T>* ba, int q, int cp) {
   for (int half = 0; half < 2; ++half) {
     const int ph = q + 7 * half;
     for (int pw = 0; pw < P; ++pw) {
-      const float g0 = ldf(stage + (2 * cp) * (P * P) + ph * P + pw) * hdr.inv_count;
-      const float g1 = ldf(stage + (2 * cp + 1) * (P * P) + ph * P + pw) * hdr.inv_count;
-      for (int iy = 0; iy < hdr.gh; ++iy) {
+      const float g0 = ldf(ba->stage + (2 * cp) * (P * P) + ph * P + pw) * ba->inv_count;
+      const float g1 = ldf(ba->stage + (2 * cp + 1) * (P * P) + ph * P + pw) * ba->inv_count;
+      for (int iy = 0; iy < ba->gh; ++iy) {
         int ylo, yhi;
         float ly, hy;
-        const bool vy = axis_tap(sample_coord(hdr.start_h, hdr.bin_h, ph, iy, hdr.gh), H, ylo, yhi, ly, hy);
-        for (int ix = 0; ix < hdr.gw; ++ix) {
+        const bool vy = axis_tap(sample_coord(ba->start_h, ba->bin_h, ph, iy, ba->gh), H, ylo, yhi, ly, hy);
+        for (int ix = 0; ix < ba->gw; ++ix) {
           int xlo, xhi;
           float lx, hx;
-          const bool vx = axis_tap(sample_coord(hdr.start_w, hdr.bin_w, pw, ix, hdr.gw), W, xlo, xhi, lx, hx);
+          const bool vx = axis_tap(sample_coord(ba->start_w, ba->bin_w, pw, ix, ba->gw), W, xlo, xhi, lx, hx);
           if (vy && vx) {
             smem_add2(pl + ylo * W + xlo, make_float2(g0 * hy * hx, g1 * hy * hx));
             smem_add2(pl + ylo * W + xhi, make_float2(g0 * hy * lx, g1 * hy * lx));
@@ -186,14 +254,7 @@ __device__ __noinline__ void bwd_task_direct(float2* __restrict__ pl, int H, int
 }
 
 template <typename T>
-struct BwdArea {
-  WarpArea<T> wa;
-  uint64_t bar;
-  uint64_t pad;
-};
-
-template <typename T>
-__global__ void __launch_bounds__(NTHREADS, 1) roi_align_bwd_slab2(const Params p, float* __restrict__ gfeat32) {
+__global__ void __launch_bounds__(BNTHREADS, 1) roi_align_bwd_slab2(const Params p, float* __restrict__ gfeat32) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* slab = reinterpret_cast<float*>(smem_raw);
   const size_t slab_bytes = (size_t)NPAIR * p.pair_stride * sizeof(float2);
@@ -202,13 +263,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) roi_align_bwd_slab2(const Params 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   BwdArea<T>* ba = areas + warp;
-  WarpArea<T>* wa = &ba->wa;
   const int nslab = p.C / CS;
   const int HW = p.H * p.W;
   const T* gout = reinterpret_cast<const T*>(p.feat);  // grad_out [R,C,14,14]
-  const int q = lane >> 2, cp = lane & 3;
-  float2* pl = reinterpret_cast<float2*>(slab) + (size_t)cp * p.pair_stride;
+  float2* tile = reinterpret_cast<float2*>(slab);
   uint32_t parity = 0;
+  constexpr uint32_t BLOCK_BYTES = CS * P * P * sizeof(T);
   if (lane == 0) mbar_init(&ba->bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
@@ -227,43 +287,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) roi_align_bwd_slab2(const Params 
     const int r0 = (int)(local - (long long)k * Rn);
     const long long seg_end_u = min(u_end, (long long)r_base * nslab + (long long)(k + 1) * Rn);
     const int r1 = r0 + (int)(seg_end_u - u);
+    const T* gbase = gout + ((long long)r_base * p.C + (long long)k * CS) * (P * P);
+    const long long roi_stride = (long long)p.C * (P * P);
 
-    for (int i = tid; i < NPAIR * p.pair_stride * 2; i += NTHREADS) slab[i] = 0.f;
+    for (int i = tid; i < NPAIR * p.pair_stride * 2; i += BNTHREADS) slab[i] = 0.f;
     if (tid == 0) s_next = r0;
     __syncthreads();
 
-    while (true) {
-      int r = 0;
-      if (lane == 0) r = atomicAdd(&s_next, 1);
-      r = __shfl_sync(0xffffffffu, r, 0);
-      if (r >= r1) break;
+    int r = 0;
+    if (lane == 0) r = atomicAdd(&s_next, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    while (r < r1) {
+      int rn = 0;
       if (lane == 0) {
-        mbar_expect_tx(&ba->bar, (uint32_t)(CS * P * P * sizeof(T)));
-        bulk_load(wa->stage, gout + ((long long)(r_base + r) * p.C + (long long)k * CS) * (P * P),
-                  (uint32_t)(CS * P * P * sizeof(T)), &ba->bar);
+        mbar_expect_tx(&ba->bar, BLOCK_BYTES);
+        bulk_load(ba->stage, gbase + (long long)r * roi_stride, BLOCK_BYTES, &ba->bar);
+        rn = atomicAdd(&s_next, 1);
+        if (rn < r1) bulk_prefetch_l2(gbase + (long long)rn * roi_stride, BLOCK_BYTES);
       }
-      build_tables<T>(p.rois + (long long)(r_base + r) * 5, p, wa, lane);
+      rn = __shfl_sync(0xffffffffu, rn, 0);
+      build_bwd_tables<T>(p.rois + (long long)(r_base + r) * 5, p, ba, lane);
       __syncwarp();
       mbar_wait(&ba->bar, parity);
       parity ^= 1;
-      if (lane < 28) {
-        const int mode = wa->hdr.mode;
-        if (mode == 1) {
-          const int gh = wa->hdr.gh;
-          if (gh == 1) bwd_task<T, 1>(pl, wa, q, cp);
-          else if (gh == 2) bwd_task<T, 2>(pl, wa, q, cp);
-          else bwd_task<T, 0>(pl, wa, q, cp);
-        } else if (mode == 2) {
-          bwd_task_direct<T>(pl, p.H, p.W, wa->hdr, q, cp, wa->stage);
+      const int mode = ba->mode;
+      if (mode == 1) {
+        const int ntask = ba->ncols * NPAIR;
+        for (int t = lane; t < ntask; t += 32) {
+          const int cp = t & (NPAIR - 1), c = t >> 2;
+          bwd_column<T>(tile + (size_t)cp * p.pair_stride, p.W, ba, c, cp);
         }
+      } else if (mode == 2 && lane < 28) {
+        bwd_direct<T>(tile + (size_t)(lane & 3) * p.pair_stride, p.H, p.W, ba, lane >> 2, lane & 3);
       }
       __syncwarp();  // every lane is done with the staging block before the next bulk load overwrites it
+      r = rn;
     }
     __syncthreads();  // the tile is complete
-    // merge the tile into grad_feat (fp32): plain stores when this CTA owns the whole (image, slab), atomics otherwise
     float* dst = gfeat32 + ((long long)n * p.C + (long long)k * CS) * HW;
     const bool whole = (r0 == 0 && r1 == Rn);
-    for (int e = tid; e < CS * HW; e += NTHREADS) {
+    for (int e = tid; e < CS * HW; e += BNTHREADS) {
       const int c = e / HW, o = e - c * HW;
       const float v = slab[((size_t)(c >> 1) * p.pair_stride + o) * 2 + (c & 1)];
       if (whole) dst[e] = v;
@@ -286,7 +349,7 @@ __global__ void cvt_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16*
 template <typename T>
 static size_t bwd_smem_total(int HW) {
   const size_t slab_bytes = (size_t)NPAIR * pair_stride_host(HW) * sizeof(float2);
-  return ((slab_bytes + 127) / 128) * 128 + (size_t)NWARPS * sizeof(BwdArea<T>);
+  return ((slab_bytes + 127) / 128) * 128 + (size_t)BNWARPS * sizeof(BwdArea<T>);
 }
 
 }  // namespace v2
@@ -323,16 +386,14 @@ static int launch_bwd_t(const void* gout, const float* rois, float* gfeat32, int
   p.debug = 0;
   const size_t smem = v2::bwd_smem_total<T>(H * W);
   UNIT_CUDA(cudaFuncSetAttribute(v2::roi_align_bwd_slab2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // every (image, slab) must be visited even when it has few RoIs: the grid walks contiguous unit ranges
-  long long grid = p.units_total / 48;
+  long long grid = p.units_total / 44;
   if (grid < 1) grid = 1;
   if (grid > sm_count()) grid = sm_count();
-  v2::roi_align_bwd_slab2<T><<<(int)grid, v2::NTHREADS, smem, st>>>(p, gfeat32);
+  v2::roi_align_bwd_slab2<T><<<(int)grid, v2::BNTHREADS, smem, st>>>(p, gfeat32);
   UNIT_CHECK_LAUNCH("roi_align_bwd_slab2");
   return UNIT_OK;
 }
 
-// grad_feat must be zero-filled by the caller of this function (images without RoIs and split slabs rely on it).
 int launch_bwd_slab2(const void* gout, const float* rois, void* gfeat, void* f32_scratch, int N, int C, int H, int W,
                      int R, float scale, int sr, int aligned, int dtype, const int* img_off, cudaStream_t st) {
   const long long total = (long long)N * C * H * W;

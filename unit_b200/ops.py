@@ -259,6 +259,36 @@ def box_get_deltas(src: torch.Tensor, tgt: torch.Tensor, weights=(10.0, 10.0, 5.
     return out
 
 
+class _FastRCNNLossFn(torch.autograd.Function):
+    """[D2] FastRCNNOutputs.losses fused with its gradient: (loss_cls, loss_box_reg)."""
+
+    @staticmethod
+    def forward(ctx, scores, deltas, proposals, gt_boxes, gt_classes, weights, beta):
+        dev = _need_cuda(scores, deltas)
+        scores, deltas = _c(scores, _F32), _c(deltas, _F32)
+        R, K1 = scores.shape
+        losses = torch.empty((2,), dtype=_F32, device=dev)
+        d_scores = torch.empty_like(scores)
+        d_deltas = torch.empty_like(deltas)
+        ws = _workspace(dev, max(R, 1) * 8)
+        check(lib().unit_fastrcnn_loss(_ptr(scores), _ptr(deltas), _ptr(_c(proposals, _F32)), _ptr(_c(gt_boxes, _F32)),
+                                       _ptr(_c(gt_classes, torch.int64)), R, K1 - 1, float(weights[0]),
+                                       float(weights[1]), float(weights[2]), float(weights[3]), float(beta),
+                                       _ptr(losses), _ptr(d_scores), _ptr(d_deltas), _ptr(ws), ws.numel(), _stream()),
+              "unit_fastrcnn_loss")
+        ctx.save_for_backward(d_scores, d_deltas)
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_cls, g_box):
+        d_scores, d_deltas = ctx.saved_tensors
+        return d_scores * g_cls, d_deltas * g_box, None, None, None, None, None
+
+
+def fastrcnn_loss(scores, deltas, proposals, gt_boxes, gt_classes, weights=(10.0, 10.0, 5.0, 5.0), beta=0.0):
+    return _FastRCNNLossFn.apply(scores, deltas, proposals, gt_boxes, gt_classes, tuple(weights), float(beta))
+
+
 NMS_CLASSWISE, NMS_COORD_TRICK, NMS_TV_CUDA_RULE, NMS_TV_CPU_RULE = 0, 1, 2, 3
 
 

@@ -124,8 +124,16 @@ class WeakDetectorOutputsBase(nn.Module):
     # -- packed weights ---------------------------------------------------------------------------------
     def mean_oicr_weight(self):
         """mean_k(W_k x + b_k) == (mean_k W_k) x + mean_k b_k: the 3 refinement classifiers collapse to one."""
+        params = [q for p in self.oicr_predictors for q in (p.weight, p.bias)]
+        frozen = not any(q.requires_grad for q in params)
+        key = (tuple(q._version for q in params), params[0].device, params[0].data_ptr())
+        cached = self.__dict__.get("_mean_cache")
+        if frozen and cached is not None and cached[0] == key:
+            return cached[1], cached[2]
         w = torch.stack([p.weight for p in self.oicr_predictors]).mean(0)
         b = torch.stack([p.bias for p in self.oicr_predictors]).mean(0)
+        if frozen:
+            self.__dict__["_mean_cache"] = (key, w.detach(), b.detach())
         return w, b
 
     def mean_logits(self, x: torch.Tensor) -> torch.Tensor:
@@ -261,12 +269,24 @@ class SupervisedDetectorOutputsBase(nn.Module):
     def _linears(self, x: torch.Tensor):
         """One packed GEMM for every Linear that reads ``x``: [delta | bbox | (ft cls | ft bbox)]."""
         K1, K4 = self.num_classes + 1, self.num_classes * self.box_dim
-        ws = [self.cls_score_delta.weight, self.bbox_pred_delta.weight]
-        bs = [self.cls_score_delta.bias, self.bbox_pred_delta.bias]
+        base = [self.cls_score_delta.weight, self.bbox_pred_delta.weight, self.cls_score_delta.bias,
+                self.bbox_pred_delta.bias]
         ft_c, ft_b = self._ft_layers()
+        frozen = not any(q.requires_grad for q in base)
+        if frozen and ft_c is not None:
+            # fine-tuning: the frozen [delta | bbox] block is packed once; only the small trainable block is re-packed
+            key = (tuple(q._version for q in base), base[0].device, base[0].data_ptr())
+            cached = self.__dict__.get("_pack_cache")
+            if cached is None or cached[0] != key:
+                cached = (key, torch.cat(base[:2], 0).detach(), torch.cat(base[2:], 0).detach())
+                self.__dict__["_pack_cache"] = cached
+            y = F.linear(x, cached[1], cached[2])
+            yf = F.linear(x, torch.cat([ft_c.weight, ft_b.weight], 0), torch.cat([ft_c.bias, ft_b.bias], 0))
+            return y[:, :K1], y[:, K1:], yf[:, :K1], yf[:, K1:]
+        ws, bs = base[:2], base[2:]
         if ft_c is not None:
-            ws += [ft_c.weight, ft_b.weight]
-            bs += [ft_c.bias, ft_b.bias]
+            ws = ws + [ft_c.weight, ft_b.weight]
+            bs = bs + [ft_c.bias, ft_b.bias]
         y = F.linear(x, torch.cat(ws, 0), torch.cat(bs, 0))
         delta, pd = y[:, :K1], y[:, K1:K1 + K4]
         fts = ftd = None
@@ -325,24 +345,14 @@ class SupervisedDetectorOutputsBase(nn.Module):
         if train_only_weak:
             return {}
         scores, proposal_deltas = predictions
+        if self.box_reg_loss_type != "smooth_l1":
+            raise NotImplementedError("only the smooth_l1 box loss is used by the reference YAMLs")
         gt_classes = layers.cat([p.gt_classes for p in proposals])
         prop = layers.cat([p.proposal_boxes.tensor for p in proposals])
         gt_boxes = layers.cat([p.gt_boxes.tensor for p in proposals])
-        loss_cls = F.cross_entropy(scores, gt_classes, reduction="mean")
-        bg = scores.shape[1] - 1
-        fg_inds = layers.nonzero_tuple((gt_classes >= 0) & (gt_classes < bg))[0]
-        cols = self.box_dim * gt_classes[fg_inds][:, None] + torch.arange(self.box_dim, device=scores.device)
-        if self.box_reg_loss_type != "smooth_l1":
-            raise NotImplementedError("only the smooth_l1 box loss is used by the reference YAMLs")
-        target = self.box2box_transform.get_deltas(prop, gt_boxes)[fg_inds]
-        pred = proposal_deltas[fg_inds[:, None], cols]
-        n = torch.abs(pred - target)
-        if self.smooth_l1_beta < 1e-5:
-            loss_box = n.sum()
-        else:
-            b = self.smooth_l1_beta
-            loss_box = torch.where(n < b, 0.5 * n ** 2 / b, n - 0.5 * b).sum()
-        return {"loss_cls": loss_cls, "loss_box_reg": loss_box / max(gt_classes.numel(), 1)}
+        loss_cls, loss_box = ops.fastrcnn_loss(scores, proposal_deltas, prop, gt_boxes, gt_classes,
+                                               self.box2box_transform.weights, self.smooth_l1_beta)
+        return {"loss_cls": loss_cls, "loss_box_reg": loss_box}
 
     def predict_probs(self, predictions, proposals):
         scores, _ = predictions
