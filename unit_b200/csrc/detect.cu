@@ -696,10 +696,12 @@ __global__ void fastrcnn_loss_kernel(const float* __restrict__ scores, const flo
       dv = diff > 0.f ? 1.f : -1.f;
     }
   }
+  const float dv0 = __shfl_sync(0xffffffffu, dv, 0), dv1 = __shfl_sync(0xffffffffu, dv, 1);
+  const float dv2 = __shfl_sync(0xffffffffu, dv, 2), dv3 = __shfl_sync(0xffffffffu, dv, 3);
   for (int i = lane; i < 4 * K; i += 32) {
     float v = 0.f;
     const int j = i - 4 * cls;
-    if (fg && j >= 0 && j < 4) v = __shfl_sync(__activemask(), dv, j) * invR;
+    if (fg && j >= 0 && j < 4) v = (j == 0 ? dv0 : j == 1 ? dv1 : j == 2 ? dv2 : dv3) * invR;
     d_deltas[(long long)r * 4 * K + i] = v;
   }
   box_loss += __shfl_xor_sync(0xffffffffu, box_loss, 1);

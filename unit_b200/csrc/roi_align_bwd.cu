@@ -1,17 +1,15 @@
 // ROIAlign backward, slab-resident kernel.
 //
-// Same decomposition as roi_align_fwd.cu, transposed.  A persistent CTA keeps the GRADIENT tile of one
-// (image, 8-channel slab) -- channel-pair interleaved float2, 134 KB for the 50x84 map -- in shared memory.  Each of
-// its warps pulls RoIs of that slab, streams the RoI's [8][14][14] grad_out block in with one TMA bulk load
-// (cp.async.bulk.shared::cta.global + mbarrier, overlapped with the table build; the following RoI's block is
-// prefetched into L2), and scatters it column-wise: lane (c, cp) OWNS feature column x0 + c of channel pair cp for
-// this RoI.  For each of the 14 bin rows it gathers the horizontally spread value u = sum_s w_s * g[row][bin(s)] over
-// the samples touching its column (two contiguous sample ranges of the x-table), then spreads u vertically through a
-// two-row register window, so that every tile cell (y, x) of the RoI's footprint receives exactly ONE 64-bit
-// shared-memory CAS-add (both channels at once).  Lanes of a warp never collide (distinct columns / planes); only
-// different warps (different RoIs) can, and rarely.  Per RoI that is footprint-many atomics on shared memory instead
-// of torchvision's 4*gh*gw global atomics per output element (~1e9 for 2x512 RoIs).
-// The tile reaches HBM once per segment (plain stores when the CTA owns the whole (image, slab), red.global else).
+// Work item = (RoI, group of 16 eight-channel slabs), pulled from a global counter by the 15 warps of each of the 148
+// persistent CTAs.  A warp builds the RoI's sampling tables ONCE (same fp32 operation order as the forward and as
+// torchvision) and reuses them for the 16 slabs; each slab's [8][14][14] grad_out block -- 6272 contiguous bytes --
+// streams in through a double-buffered TMA bulk load (cp.async.bulk.shared::cta.global + mbarrier).
+// The scatter is column-owned: lane (pair of feature columns, channel pair) gathers, per bin row, the horizontally
+// spread values of its two columns from three consecutive lower-tap groups of the x-table, spreads them vertically
+// through a two-row register window, and emits exactly ONE 16-byte `red.global.add.v4.f32` per footprint cell pair
+// (2 columns x 2 channels) into an L2-resident, channel-pair interleaved fp32 image of grad_feat, which a final
+// streaming kernel converts to NCHW.  That is footprint/2 vector atomics per RoI and channel pair instead of
+// torchvision's 4*gh*gw scalar atomics per output element (~1e9 for 2x512 RoIs), with no shared-memory tile at all.
 #include "roi_slab.cuh"
 
 namespace unit {
@@ -20,7 +18,7 @@ namespace v2 {
 
 constexpr int BMAXG = 4;             // sampling grid handled with tables in the backward (RoI side <= 56 px)
 constexpr int BMAXS = P * BMAXG;
-constexpr int BNWARPS = 12;
+constexpr int BNWARPS = 15;
 constexpr int BNTHREADS = BNWARPS * 32;
 
 struct __align__(16) XSamp {
@@ -35,11 +33,10 @@ struct __align__(16) BwdArea {
   float inv_count, start_w, start_h, bin_w, bin_h;
   int pad[3];
   XSamp xs[BMAXS];
-  int colstart[BMAXS + 4];   // colstart[c] = first sample whose lower tap is >= x0 + c   (ncols + 1 entries)
+  int colstart[BMAXS + 8];   // colstart[c + 2] = first sample whose lower tap is >= x0 + c, for c in [-2, ncols + 1]
   float2 ys[BMAXS + 2];      // (hy | LASTROW sign, ly)
-  __align__(16) T stage[CS * P * P];
-  uint64_t bar;
-  uint64_t pad2;
+  __align__(16) T stage[2][CS * P * P];
+  uint64_t bar[2];
 };
 
 __device__ __forceinline__ void smem_add2(float2* addr, float2 v) {
@@ -124,19 +121,24 @@ __device__ __forceinline__ void build_bwd_tables(const float* __restrict__ roi, 
         e.pad = 0;
         ba->xs[s] = e;
         const int c = lo - x0;
-        if (c < 0 || c + 2 >= BMAXS + 4) {
+        if (c < 0 || c + 5 >= BMAXS + 8) {
           jump = true;  // cannot happen for unit sample steps; keeps the table writes in bounds
         } else {
-        if (s == 0) ba->colstart[0] = 0;
-        if (s < ns - 1) {
-          const int d = nlo - lo;
-          jump |= (d > 1 || d < 0);
-          if (d == 1) ba->colstart[c + 1] = s + 1;
-        } else {
-          ba->colstart[c + 1] = ns;      // end of the last lower-tap column
-          ba->colstart[c + 2] = ns;      // the column that only receives upper taps
-          ba->ncols = c + 2;
-        }
+          if (s == 0) {
+            ba->colstart[0] = 0;  // c = -2
+            ba->colstart[1] = 0;  // c = -1
+            ba->colstart[2] = 0;  // c = 0
+          }
+          if (s < ns - 1) {
+            const int d = nlo - lo;
+            jump |= (d > 1 || d < 0);
+            if (d == 1) ba->colstart[c + 3] = s + 1;
+          } else {
+            ba->colstart[c + 3] = ns;  // end of the last lower-tap column
+            ba->colstart[c + 4] = ns;  // the column that only receives upper taps
+            ba->colstart[c + 5] = ns;
+            ba->ncols = c + 2;
+          }
         }
       }
     }
@@ -186,53 +188,73 @@ __device__ __forceinline__ void build_bwd_tables(const float* __restrict__ roi, 
   }
 }
 
-// lane task: feature column x0 + c of channel pair cp
+// lane task: feature columns (xA, xA+1) (xA even) of channel pair cp.  cA = xA - x0 may be -1.
+// Gathers, per bin row, the horizontally spread values of both columns from three consecutive lower-tap groups of
+// the x-table, spreads them vertically through a two-row register window, and issues ONE 16-byte
+// red.global.add.v4.f32 per (row, column pair) into the pair-interleaved fp32 scratch image.
 template <typename T>
-__device__ __forceinline__ void bwd_column(float2* __restrict__ tile_pair, int W, const BwdArea<T>* ba, int c, int cp) {
+__device__ __forceinline__ void bwd_column_pair(float* __restrict__ scratch_pair, int W, const BwdArea<T>* ba,
+                                                const T* __restrict__ stage, int cA, int cp) {
   const int gh = ba->gh;
-  const int cs0 = c > 0 ? ba->colstart[c - 1] : 0;
-  const int cs1 = ba->colstart[c];
-  const int cs2 = ba->colstart[c + 1];
-  const int lo_begin = c > 0 ? cs0 : cs1;  // samples [lo_begin, cs1) contribute through their upper tap
-  const T* g0 = ba->stage + (2 * cp) * (P * P);
+  const int* cs = ba->colstart + 2;  // cs[c] valid for c in [-2, ncols + 1]
+  const int s0 = cs[cA - 1], s1 = cs[cA], s2 = cs[cA + 1], s3 = cs[cA + 2];
+  const T* g0 = stage + (2 * cp) * (P * P);
   const T* g1 = g0 + P * P;
-  float2* cell = tile_pair + ba->y0 * W + ba->x0 + c;
-  float2 dlo = make_float2(0.f, 0.f), dhi = dlo;
+  float* cell = scratch_pair + ((size_t)ba->y0 * W + (ba->x0 + cA)) * 2;
+  float2 loA = make_float2(0.f, 0.f), loB = loA, hiA = loA, hiB = loA;
   const float2* ys = ba->ys;
   for (int ph = 0; ph < P; ++ph) {
-    float2 u = make_float2(0.f, 0.f);
+    float2 uA = make_float2(0.f, 0.f), uB = uA;
     const T* r0 = g0 + ph * P;
     const T* r1 = g1 + ph * P;
-    for (int s = lo_begin; s < cs1; ++s) {
+    for (int s = s0; s < s1; ++s) {
       const XSamp e = ba->xs[s];
-      u = ffma2(e.l, make_float2(ldf(r0 + e.pw), ldf(r1 + e.pw)), u);
+      uA = ffma2(e.l, make_float2(ldf(r0 + e.pw), ldf(r1 + e.pw)), uA);
     }
-    for (int s = cs1; s < cs2; ++s) {
+    for (int s = s1; s < s2; ++s) {
       const XSamp e = ba->xs[s];
-      u = ffma2(e.h, make_float2(ldf(r0 + e.pw), ldf(r1 + e.pw)), u);
+      const float2 g = make_float2(ldf(r0 + e.pw), ldf(r1 + e.pw));
+      uA = ffma2(e.h, g, uA);
+      uB = ffma2(e.l, g, uB);
+    }
+    for (int s = s2; s < s3; ++s) {
+      const XSamp e = ba->xs[s];
+      uB = ffma2(e.h, make_float2(ldf(r0 + e.pw), ldf(r1 + e.pw)), uB);
     }
     for (int iy = 0; iy < gh; ++iy) {
       const float2 t = *ys++;
-      dlo = ffma2(fabsf(t.x), u, dlo);
-      dhi = ffma2(t.y, u, dhi);
+      const float hy = fabsf(t.x);
+      loA = ffma2(hy, uA, loA);
+      loB = ffma2(hy, uB, loB);
+      hiA = ffma2(t.y, uA, hiA);
+      hiB = ffma2(t.y, uB, hiB);
       if (__float_as_uint(t.x) >> 31) {
-        if (dlo.x != 0.f || dlo.y != 0.f) smem_add2(cell, dlo);
-        cell += W;
-        dlo = dhi;
-        dhi = make_float2(0.f, 0.f);
+        if (loA.x != 0.f || loA.y != 0.f || loB.x != 0.f || loB.y != 0.f)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "f"(loA.x), "f"(loA.y),
+                       "f"(loB.x), "f"(loB.y)
+                       : "memory");
+        cell += 2 * W;
+        loA = hiA;
+        loB = hiB;
+        hiA = make_float2(0.f, 0.f);
+        hiB = make_float2(0.f, 0.f);
       }
     }
   }
-  if (dlo.x != 0.f || dlo.y != 0.f) smem_add2(cell, dlo);  // the row that only receives upper taps
+  if (loA.x != 0.f || loA.y != 0.f || loB.x != 0.f || loB.y != 0.f)
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "f"(loA.x), "f"(loA.y), "f"(loB.x),
+                 "f"(loB.y)
+                 : "memory");
 }
 
 template <typename T>
-__device__ __noinline__ void bwd_direct(float2* __restrict__ pl, int H, int W, const BwdArea<T>* ba, int q, int cp) {
+__device__ __noinline__ void bwd_direct(float* __restrict__ scratch_pair, int H, int W, const BwdArea<T>* ba,
+                                        const T* __restrict__ stage, int q, int cp) {
   for (int half = 0; half < 2; ++half) {
     const int ph = q + 7 * half;
     for (int pw = 0; pw < P; ++pw) {
-      const float g0 = ldf(ba->stage + (2 * cp) * (P * P) + ph * P + pw) * ba->inv_count;
-      const float g1 = ldf(ba->stage + (2 * cp + 1) * (P * P) + ph * P + pw) * ba->inv_count;
+      const float g0 = ldf(stage + (2 * cp) * (P * P) + ph * P + pw) * ba->inv_count;
+      const float g1 = ldf(stage + (2 * cp + 1) * (P * P) + ph * P + pw) * ba->inv_count;
       for (int iy = 0; iy < ba->gh; ++iy) {
         int ylo, yhi;
         float ly, hy;
@@ -242,10 +264,13 @@ __device__ __noinline__ void bwd_direct(float2* __restrict__ pl, int H, int W, c
           float lx, hx;
           const bool vx = axis_tap(sample_coord(ba->start_w, ba->bin_w, pw, ix, ba->gw), W, xlo, xhi, lx, hx);
           if (vy && vx) {
-            smem_add2(pl + ylo * W + xlo, make_float2(g0 * hy * hx, g1 * hy * hx));
-            smem_add2(pl + ylo * W + xhi, make_float2(g0 * hy * lx, g1 * hy * lx));
-            smem_add2(pl + yhi * W + xlo, make_float2(g0 * ly * hx, g1 * ly * hx));
-            smem_add2(pl + yhi * W + xhi, make_float2(g0 * ly * lx, g1 * ly * lx));
+            const int idx[4] = {ylo * W + xlo, ylo * W + xhi, yhi * W + xlo, yhi * W + xhi};
+            const float w[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              atomicAdd(scratch_pair + 2 * (size_t)idx[k], g0 * w[k]);
+              atomicAdd(scratch_pair + 2 * (size_t)idx[k] + 1, g1 * w[k]);
+            }
           }
         }
       }
@@ -253,87 +278,87 @@ __device__ __noinline__ void bwd_direct(float2* __restrict__ pl, int H, int W, c
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(BNTHREADS, 1) roi_align_bwd_slab2(const Params p, float* __restrict__ gfeat32) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* slab = reinterpret_cast<float*>(smem_raw);
-  const size_t slab_bytes = (size_t)NPAIR * p.pair_stride * sizeof(float2);
-  BwdArea<T>* areas = reinterpret_cast<BwdArea<T>*>(smem_raw + ((slab_bytes + 127) / 128) * 128);
-  __shared__ int s_next;
+constexpr int SLABS_PER_ITEM = 16;  // a warp reuses one RoI's tables for 16 consecutive 8-channel slabs
 
+template <typename T>
+__global__ void __launch_bounds__(BNTHREADS, 1)
+roi_align_bwd_slab2(const Params p, float* __restrict__ scratch, int* __restrict__ item_counter) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BwdArea<T>* areas = reinterpret_cast<BwdArea<T>*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   BwdArea<T>* ba = areas + warp;
   const int nslab = p.C / CS;
   const int HW = p.H * p.W;
   const T* gout = reinterpret_cast<const T*>(p.feat);  // grad_out [R,C,14,14]
-  float2* tile = reinterpret_cast<float2*>(slab);
-  uint32_t parity = 0;
   constexpr uint32_t BLOCK_BYTES = CS * P * P * sizeof(T);
-  if (lane == 0) mbar_init(&ba->bar, 1);
+  uint32_t parity = 0;  // bit b = phase parity of barrier b
+  if (lane == 0) {
+    mbar_init(&ba->bar[0], 1);
+    mbar_init(&ba->bar[1], 1);
+  }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
+  __syncwarp();
 
-  const long long u_begin = p.units_total * blockIdx.x / gridDim.x;
-  const long long u_end = p.units_total * (blockIdx.x + 1) / gridDim.x;
-  long long u = u_begin;
-  int n = 0;
-  while (u < u_end) {
-    while (n < p.N && (long long)p.img_off[n + 1] * nslab <= u) ++n;
-    if (n >= p.N) break;
-    const int r_base = p.img_off[n];
-    const int Rn = p.img_off[n + 1] - r_base;
-    const long long local = u - (long long)r_base * nslab;
-    const int k = (int)(local / Rn);
-    const int r0 = (int)(local - (long long)k * Rn);
-    const long long seg_end_u = min(u_end, (long long)r_base * nslab + (long long)(k + 1) * Rn);
-    const int r1 = r0 + (int)(seg_end_u - u);
-    const T* gbase = gout + ((long long)r_base * p.C + (long long)k * CS) * (P * P);
-    const long long roi_stride = (long long)p.C * (P * P);
-
-    for (int i = tid; i < NPAIR * p.pair_stride * 2; i += BNTHREADS) slab[i] = 0.f;
-    if (tid == 0) s_next = r0;
-    __syncthreads();
-
-    int r = 0;
-    if (lane == 0) r = atomicAdd(&s_next, 1);
-    r = __shfl_sync(0xffffffffu, r, 0);
-    while (r < r1) {
-      int rn = 0;
-      if (lane == 0) {
-        mbar_expect_tx(&ba->bar, BLOCK_BYTES);
-        bulk_load(ba->stage, gbase + (long long)r * roi_stride, BLOCK_BYTES, &ba->bar);
-        rn = atomicAdd(&s_next, 1);
-        if (rn < r1) bulk_prefetch_l2(gbase + (long long)rn * roi_stride, BLOCK_BYTES);
+  const int groups = (nslab + SLABS_PER_ITEM - 1) / SLABS_PER_ITEM;
+  const long long n_items = (long long)p.R * groups;
+  while (true) {
+    long long item = 0;
+    if (lane == 0) item = atomicAdd(item_counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_items) break;
+    const int r = (int)(item / groups);
+    const int k0 = (int)(item - (long long)r * groups) * SLABS_PER_ITEM;
+    const int k1 = min(nslab, k0 + SLABS_PER_ITEM);
+    const float* roi = p.rois + (long long)r * 5;
+    const int n = (int)roi[0];
+    const T* gbase = gout + (long long)r * p.C * (P * P);
+    if (lane == 0) {
+      for (int j = 0; j < 2 && k0 + j < k1; ++j) {
+        mbar_expect_tx(&ba->bar[j], BLOCK_BYTES);
+        bulk_load(ba->stage[j], gbase + (long long)(k0 + j) * CS * (P * P), BLOCK_BYTES, &ba->bar[j]);
       }
-      rn = __shfl_sync(0xffffffffu, rn, 0);
-      build_bwd_tables<T>(p.rois + (long long)(r_base + r) * 5, p, ba, lane);
-      __syncwarp();
-      mbar_wait(&ba->bar, parity);
-      parity ^= 1;
-      const int mode = ba->mode;
-      if (mode == 1) {
-        const int ntask = ba->ncols * NPAIR;
-        for (int t = lane; t < ntask; t += 32) {
-          const int cp = t & (NPAIR - 1), c = t >> 2;
-          bwd_column<T>(tile + (size_t)cp * p.pair_stride, p.W, ba, c, cp);
+    }
+    build_bwd_tables<T>(roi, p, ba, lane);
+    __syncwarp();
+    const int mode = ba->mode;
+    const bool in_img = n >= 0 && n < p.N;
+    const int xe = ba->x0 & ~1;                                   // even column the first pair starts at
+    const int npair = mode == 1 ? ((ba->x0 + ba->ncols - 1 - xe) >> 1) + 1 : 0;
+    for (int k = k0; k < k1; ++k) {
+      const int buf = (k - k0) & 1;
+      mbar_wait(&ba->bar[buf], (parity >> buf) & 1u);
+      parity ^= 1u << buf;
+      float* spair_base = scratch + ((size_t)n * (p.C / 2) + (size_t)k * NPAIR) * HW * 2;
+      if (in_img) {
+        if (mode == 1) {
+          const int ntask = npair * NPAIR;
+          for (int t = lane; t < ntask; t += 32) {
+            const int cp = t & (NPAIR - 1), pr = t >> 2;
+            bwd_column_pair<T>(spair_base + (size_t)cp * HW * 2, p.W, ba, ba->stage[buf], xe + 2 * pr - ba->x0, cp);
+          }
+        } else if (mode == 2 && lane < 28) {
+          bwd_direct<T>(spair_base + (size_t)(lane & 3) * HW * 2, p.H, p.W, ba, ba->stage[buf], lane >> 2, lane & 3);
         }
-      } else if (mode == 2 && lane < 28) {
-        bwd_direct<T>(tile + (size_t)(lane & 3) * p.pair_stride, p.H, p.W, ba, lane >> 2, lane & 3);
       }
-      __syncwarp();  // every lane is done with the staging block before the next bulk load overwrites it
-      r = rn;
+      __syncwarp();  // every lane is done with this staging buffer
+      if (lane == 0 && k + 2 < k1) {
+        mbar_expect_tx(&ba->bar[buf], BLOCK_BYTES);
+        bulk_load(ba->stage[buf], gbase + (long long)(k + 2) * CS * (P * P), BLOCK_BYTES, &ba->bar[buf]);
+      }
     }
-    __syncthreads();  // the tile is complete
-    float* dst = gfeat32 + ((long long)n * p.C + (long long)k * CS) * HW;
-    const bool whole = (r0 == 0 && r1 == Rn);
-    for (int e = tid; e < CS * HW; e += BNTHREADS) {
-      const int c = e / HW, o = e - c * HW;
-      const float v = slab[((size_t)(c >> 1) * p.pair_stride + o) * 2 + (c & 1)];
-      if (whole) dst[e] = v;
-      else if (v != 0.f) atomicAdd(dst + e, v);
-    }
-    __syncthreads();
-    u = seg_end_u;
+  }
+}
+
+// scratch [N][C/2][HW][2] fp32 -> grad_feat [N][C][HW] (T)
+template <typename T>
+__global__ void unpair_kernel(const float2* __restrict__ scratch, T* __restrict__ out, long long n_pairs_hw, int HW) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pairs_hw;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pair = i / HW;
+    const int o = (int)(i - pair * HW);
+    const float2 v = scratch[i];
+    stf(out + (2 * pair) * HW + o, v.x);
+    stf(out + (2 * pair + 1) * HW + o, v.y);
   }
 }
 
@@ -347,32 +372,29 @@ __global__ void cvt_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16*
 }
 
 template <typename T>
-static size_t bwd_smem_total(int HW) {
-  const size_t slab_bytes = (size_t)NPAIR * pair_stride_host(HW) * sizeof(float2);
-  return ((slab_bytes + 127) / 128) * 128 + (size_t)BNWARPS * sizeof(BwdArea<T>);
-}
+static size_t bwd_smem_total() { return (size_t)BNWARPS * sizeof(BwdArea<T>); }
 
 }  // namespace v2
 
 bool bwd_slab2_fits(int C, int H, int W, int dtype) {
-  if (C % v2::CS) return false;
-  const size_t need = dtype == UNIT_F32 ? v2::bwd_smem_total<float>(H * W) : v2::bwd_smem_total<__nv_bfloat16>(H * W);
-  return need <= 227 * 1024;
+  (void)dtype;
+  return (C % v2::CS) == 0 && (W % 2) == 0 && H >= 2 && W >= 2;
 }
 
-// bf16 needs an fp32 accumulation image of grad_feat: N*C*H*W*4 bytes after the offsets
+// fp32 pair-interleaved accumulation image of grad_feat + the work-item counter
 size_t bwd_slab2_workspace_bytes(int N, int C, int H, int W, int dtype) {
-  return dtype == UNIT_BF16 ? (size_t)N * C * H * W * 4 : 0;
+  (void)dtype;
+  return (size_t)N * C * H * W * 4 + 256;
 }
 
 template <typename T>
-static int launch_bwd_t(const void* gout, const float* rois, float* gfeat32, int N, int C, int H, int W, int R,
-                        float scale, int sr, int aligned, const int* img_off, cudaStream_t st) {
+static int launch_bwd_t(const void* gout, const float* rois, void* gfeat, void* ws, int N, int C, int H, int W, int R,
+                        float scale, int sr, int aligned, cudaStream_t st) {
   v2::Params p;
   p.feat = gout;
   p.rois = rois;
   p.out = nullptr;
-  p.img_off = img_off;
+  p.img_off = nullptr;
   p.N = N;
   p.C = C;
   p.H = H;
@@ -381,35 +403,33 @@ static int launch_bwd_t(const void* gout, const float* rois, float* gfeat32, int
   p.scale = scale;
   p.sampling_ratio = sr;
   p.aligned = aligned;
-  p.pair_stride = v2::pair_stride_host(H * W);
-  p.units_total = (long long)R * (C / v2::CS);
+  p.pair_stride = 0;
+  p.units_total = 0;
   p.debug = 0;
-  const size_t smem = v2::bwd_smem_total<T>(H * W);
+  const long long total = (long long)N * C * H * W;
+  int* counter = (int*)ws;
+  float* scratch = (float*)((char*)ws + 256);
+  const int zgrid = (int)std::min<long long>((total + 64 + 255) / 256, (long long)sm_count() * 8);
+  v2::zero_f32_kernel<<<zgrid, 256, 0, st>>>((float*)ws, total + 64);
+  UNIT_CHECK_LAUNCH("zero_f32_kernel");
+  const size_t smem = v2::bwd_smem_total<T>();
   UNIT_CUDA(cudaFuncSetAttribute(v2::roi_align_bwd_slab2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  long long grid = p.units_total / 44;
-  if (grid < 1) grid = 1;
+  const int groups = (C / v2::CS + v2::SLABS_PER_ITEM - 1) / v2::SLABS_PER_ITEM;
+  long long grid = ((long long)R * groups + v2::BNWARPS - 1) / v2::BNWARPS;
   if (grid > sm_count()) grid = sm_count();
-  v2::roi_align_bwd_slab2<T><<<(int)grid, v2::BNTHREADS, smem, st>>>(p, gfeat32);
+  if (grid < 1) grid = 1;
+  v2::roi_align_bwd_slab2<T><<<(int)grid, v2::BNTHREADS, smem, st>>>(p, scratch, counter);
   UNIT_CHECK_LAUNCH("roi_align_bwd_slab2");
+  v2::unpair_kernel<T><<<zgrid, 256, 0, st>>>((const float2*)scratch, (T*)gfeat, total / 2, H * W);
+  UNIT_CHECK_LAUNCH("unpair_kernel");
   return UNIT_OK;
 }
 
-int launch_bwd_slab2(const void* gout, const float* rois, void* gfeat, void* f32_scratch, int N, int C, int H, int W,
-                     int R, float scale, int sr, int aligned, int dtype, const int* img_off, cudaStream_t st) {
-  const long long total = (long long)N * C * H * W;
-  const int zgrid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
-  if (dtype == UNIT_F32) {
-    v2::zero_f32_kernel<<<zgrid, 256, 0, st>>>((float*)gfeat, total);
-    UNIT_CHECK_LAUNCH("zero_f32_kernel");
-    return launch_bwd_t<float>(gout, rois, (float*)gfeat, N, C, H, W, R, scale, sr, aligned, img_off, st);
-  }
-  v2::zero_f32_kernel<<<zgrid, 256, 0, st>>>((float*)f32_scratch, total);
-  UNIT_CHECK_LAUNCH("zero_f32_kernel");
-  int rc = launch_bwd_t<__nv_bfloat16>(gout, rois, (float*)f32_scratch, N, C, H, W, R, scale, sr, aligned, img_off, st);
-  if (rc) return rc;
-  v2::cvt_f32_bf16_kernel<<<zgrid, 256, 0, st>>>((const float*)f32_scratch, (__nv_bfloat16*)gfeat, total);
-  UNIT_CHECK_LAUNCH("cvt_f32_bf16_kernel");
-  return UNIT_OK;
+int launch_bwd_slab2(const void* gout, const float* rois, void* gfeat, void* ws, int N, int C, int H, int W, int R,
+                     float scale, int sr, int aligned, int dtype, const int* img_off, cudaStream_t st) {
+  (void)img_off;
+  if (dtype == UNIT_F32) return launch_bwd_t<float>(gout, rois, gfeat, ws, N, C, H, W, R, scale, sr, aligned, st);
+  return launch_bwd_t<__nv_bfloat16>(gout, rois, gfeat, ws, N, C, H, W, R, scale, sr, aligned, st);
 }
 
 }  // namespace roi
