@@ -191,6 +191,13 @@ int unit_similarity_transfer_bwd(const unit_transfer_params* p, const float* s_c
                                  const float* g_bbox, int detach_transfer, float* g_delta_scores,
                                  float* g_proposal_deltas, unit_stream_t stream);
 
+/* Predictor GEMM on tcgen05 tensor cores: y[M,N] = x[M,K] . w[N,K]^T + bias[N], fp32 in / fp32 out, TF32 multiply
+ * with fp32 accumulation in TMEM (TMA-fed, split-K with a deterministic reduction).  Replaces the packed nn.Linear
+ * calls of fast_rcnn.py:386-392,488-489 and weak_detector_fast_rcnn.py:172-175.  K % 4 == 0; bias nullable. */
+size_t unit_predictor_gemm_workspace_bytes(int M, int N, int K);
+int unit_predictor_gemm(const float* x, const float* w, const float* bias, float* y, int M, int N, int K,
+                        void* workspace, size_t workspace_bytes, unit_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Mask transfer + class select + sigmoid.  Replaces mask_head.py:16-37 / 72-94 and [D2] mask_rcnn_inference.
  *   logits [D,K,M,M]; s_seg [D,Nn,B] (s_is_2d: [Nn,B]); x_delta [D,K,M,M] nullable; pred_classes int64 [D].

@@ -41,6 +41,11 @@ def registry():
     return ROI_BOX_HEAD_REGISTRY
 
 
+def set_precision(head, precision):
+    head.box_predictor.gemm_precision = precision
+    head.box_predictor.weak_detector_head.gemm_precision = precision
+
+
 def _build(yaml_name, channels, registry, extra=()):
     from unit_b200.config import load_cfg
     from unit_b200.roi_heads import build_roi_heads
@@ -50,6 +55,7 @@ def _build(yaml_name, channels, registry, extra=()):
                    ["MODEL.ROI_BOX_HEAD.NAME", "StandInBoxHead", "MODEL.ROI_HEADS.EMBEDDING_PATH",
                     os.path.join(ROOT, "tests", "golden", "glove_mean.pt")] + list(extra))
     head = build_roi_heads(cfg, {"res4": ShapeSpec(channels=channels, stride=16)})
+    set_precision(head, "fp32")  # strict 1e-5 parity checks; the TF32 tensor-core GEMM is checked in test_gemm_gpu.py
     return cfg, head
 
 

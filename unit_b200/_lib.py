@@ -55,12 +55,10 @@ _SIGNATURES = {
     "unit_similarity_transfer_bwd": (c_int, [POINTER(TransferParams), P, P, P, P, P, P, P, c_int, P, P, P]),
     "unit_mask_transfer": (c_int, [P, P, c_int, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "unit_mask_paste": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, P, P]),
-}
-# optional symbols (present once csrc/gemm.cu is built)
-_OPTIONAL = {
     "unit_predictor_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "unit_predictor_gemm": (c_int, [P, P, P, P, c_int, c_int, c_int, P, c_size_t, P]),
 }
+_OPTIONAL = {}
 
 _lib = None
 

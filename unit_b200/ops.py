@@ -486,6 +486,46 @@ def similarity_transfer(spec: TransferSpec, vis_logits, delta_scores, proposal_d
                              bool(do_transfer), bool(novel_neg_inf), bool(detach_transfer))
 
 
+# ------------------------------------------------------------------------------------------------- predictor GEMM
+def predictor_gemm_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """y = x @ w.T + bias on the tcgen05 tensor cores (TF32 multiply, fp32 accumulate in TMEM)."""
+    dev = _need_cuda(x, w)
+    x, w = _c(x, _F32), _c(w, _F32)
+    b = None if bias is None else _c(bias, _F32)
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), dtype=_F32, device=dev)
+    if M == 0:
+        return y
+    ws_bytes = lib().unit_predictor_gemm_workspace_bytes(M, N, K)
+    ws = _workspace(dev, ws_bytes)
+    check(lib().unit_predictor_gemm(_ptr(x), _ptr(w), _ptr(b), _ptr(y), M, N, K, _ptr(ws), ws.numel(), _stream()),
+          "unit_predictor_gemm")
+    return y
+
+
+class _LinearTF32Fn(torch.autograd.Function):
+    """Forward on the hand-written tcgen05 GEMM; the weight/bias gradients are plain library GEMMs (cuBLAS)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return predictor_gemm_forward(x, w, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gx = gy @ w if ctx.needs_input_grad[0] else None
+        gw = gy.t() @ x if ctx.needs_input_grad[1] else None
+        gb = gy.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb
+
+
+def linear_tf32(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _LinearTF32Fn.apply(x, w, bias)
+
+
 # ------------------------------------------------------------------------------------------------- masks
 def mask_transfer(logits: torch.Tensor, s_seg: Optional[torch.Tensor], spec: TransferSpec,
                   x_delta: Optional[torch.Tensor] = None, pred_classes: Optional[torch.Tensor] = None,

@@ -30,6 +30,13 @@ def _freeze(module: nn.Module, layers_to_freeze: Sequence[str]) -> None:
             param.requires_grad = False
 
 
+def _linear(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, precision: str) -> torch.Tensor:
+    """Predictor GEMM: "tf32" = hand-written tcgen05 kernel (north_star tolerance 1e-2), "fp32" = cuBLAS fp32."""
+    if precision == "tf32" and x.is_cuda and x.dtype == torch.float32 and x.shape[1] % 4 == 0:
+        return ops.linear_tf32(x, w, b)
+    return F.linear(x, w, b)
+
+
 def _input_size(input_shape) -> int:
     if isinstance(input_shape, int):
         input_shape = ShapeSpec(channels=input_shape)
@@ -136,9 +143,11 @@ class WeakDetectorOutputsBase(nn.Module):
             self.__dict__["_mean_cache"] = (key, w.detach(), b.detach())
         return w, b
 
+    gemm_precision = "tf32"
+
     def mean_logits(self, x: torch.Tensor) -> torch.Tensor:
         w, b = self.mean_oicr_weight()
-        return F.linear(x, w, b)
+        return _linear(x, w, b, self.gemm_precision)
 
     def evaluation(self, x_weak: torch.Tensor):
         """weak_detector_fast_rcnn.py:167-187: ([list of OICR logits], zeros box deltas), None."""
@@ -195,6 +204,7 @@ class SupervisedDetectorOutputsBase(nn.Module):
     similarity=None) -> ([scores, bbox], weak_branch_return)``."""
 
     KIND = "Base"
+    gemm_precision = "tf32"  # "fp32" routes the predictor GEMMs through cuBLAS fp32 (strict 1e-5 parity checks)
 
     @configurable
     def __init__(self, input_shape, *, box2box_transform, num_classes, test_score_thresh=0.0, test_nms_thresh=0.5,
@@ -280,14 +290,15 @@ class SupervisedDetectorOutputsBase(nn.Module):
             if cached is None or cached[0] != key:
                 cached = (key, torch.cat(base[:2], 0).detach(), torch.cat(base[2:], 0).detach())
                 self.__dict__["_pack_cache"] = cached
-            y = F.linear(x, cached[1], cached[2])
-            yf = F.linear(x, torch.cat([ft_c.weight, ft_b.weight], 0), torch.cat([ft_c.bias, ft_b.bias], 0))
+            y = _linear(x, cached[1], cached[2], self.gemm_precision)
+            yf = _linear(x, torch.cat([ft_c.weight, ft_b.weight], 0), torch.cat([ft_c.bias, ft_b.bias], 0),
+                         self.gemm_precision)
             return y[:, :K1], y[:, K1:], yf[:, :K1], yf[:, K1:]
         ws, bs = base[:2], base[2:]
         if ft_c is not None:
             ws = ws + [ft_c.weight, ft_b.weight]
             bs = bs + [ft_c.bias, ft_b.bias]
-        y = F.linear(x, torch.cat(ws, 0), torch.cat(bs, 0))
+        y = _linear(x, torch.cat(ws, 0), torch.cat(bs, 0), self.gemm_precision)
         delta, pd = y[:, :K1], y[:, K1:K1 + K4]
         fts = ftd = None
         if ft_c is not None:
