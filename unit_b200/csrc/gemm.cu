@@ -183,12 +183,12 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
 // Y[m][n] = bias[n] + sum_s partial[s][m][n]   (fixed summation order)
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
-                                     float* __restrict__ out, int M, int N, int ldp, int splits) {
+                                     float* __restrict__ out, int M, int MP, int N, int ldp, int splits) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)M * N) return;
   const int m = (int)(i / N), n = (int)(i - (long long)m * N);
   float acc = bias ? bias[n] : 0.f;
-  for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * M + m) * ldp + n];
+  for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * MP + m) * ldp + n];
   out[i] = acc;
 }
 
@@ -276,7 +276,7 @@ int unit_predictor_gemm(const float* x, const float* w, const float* bias, float
   tf32_gemm_kernel<<<grid, 128, smem, st>>>(map_a, map_b, p);
   UNIT_CHECK_LAUNCH("tf32_gemm_kernel");
   const long long total = (long long)M * N;
-  splitk_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(p.partial, bias, y, M, N, p.n_tiles * p.NP, p.splits);
+  splitk_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(p.partial, bias, y, M, mp, N, p.n_tiles * p.NP, p.splits);
   UNIT_CHECK_LAUNCH("splitk_reduce_kernel");
   return UNIT_OK;
 }
