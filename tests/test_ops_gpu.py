@@ -107,6 +107,28 @@ def test_roi_align_backward_matches_torchvision(ops, shape):
     assert_close_rms(feat2.grad.cpu(), ref, 1e-5, "roi_align bwd (generic)")
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 50, 84, 96, 0), (1, 128, 20, 30, 40, 0), (2, 64, 50, 84, 48, 2),
+                                   (1, 64, 120, 200, 24, 0), (3, 192, 7, 9, 10, 0)])
+def test_roi_align_backward_channel_lane(ops, shape):
+    """C % 64 == 0 takes the channel-lane backward (roi_align_bwd_cl.cu): adaptive and fixed sampling grids, RoIs
+    hanging over every image border, degenerate and whole-image RoIs (grid > 6 -> direct path), unsorted RoIs."""
+    n, c, h, w, per, sr = shape
+    g = seeded(300 + c + h)
+    rois = _rois(n, per, h * 16, w * 16, g)
+    rois[0, 1:] = torch.tensor([-40.0, -30.0, 100.0, 90.0])
+    rois[1, 1:] = torch.tensor([0.0, 0.0, w * 16.0, h * 16.0])                 # whole image
+    rois[2, 1:] = torch.tensor([w * 16.0 - 20, h * 16.0 - 20, w * 16.0 + 60, h * 16.0 + 50])
+    rois[3, 1:] = torch.tensor([33.0, 47.0, 33.0, 47.0])                       # zero-size
+    rois[4, 1:] = torch.tensor([-500.0, -500.0, -100.0, -100.0])               # entirely outside
+    rois[5, 1:] = torch.tensor([5.0, 5.0, 9.0, w * 4.0])                        # thin
+    rois = rois[torch.randperm(rois.shape[0], generator=g)]
+    gout = torch.randn(rois.shape[0], c, 14, 14, generator=g)
+    ref = torch.ops.torchvision._roi_align_backward(gout, rois, 1.0 / 16, 14, 14, n, c, h, w, sr, True)
+    mag = torch.ops.torchvision._roi_align_backward(gout.abs(), rois, 1.0 / 16, 14, 14, n, c, h, w, sr, True)
+    got = ops.roi_align_backward(gout.cuda(), rois.cuda(), (n, c, h, w), 1.0 / 16, sr, True, False)
+    assert_close_rms(got.cpu(), ref, 1e-5, "roi_align bwd (channel-lane)", magnitude=mag)
+
+
 def test_roi_align_linearity_full_size(ops):
     """Size-independent property at BASELINE.json's full size: ROIAlign is linear in the feature map, and
     <roi_align(f), g> == <f, roi_align_bwd(g)> (adjointness of forward and backward)."""
