@@ -200,6 +200,52 @@ def test_finetune_train_step_grads_vs_oracle(registry):
     assert pred.cls_score_delta.weight.grad is None  # frozen by FREEZE_LAYERS.FAST_RCNN
 
 
+def test_graphed_train_step_matches_eager(registry):
+    """RoIStage.train_step_graphed (two CUDA graphs around the host draw) == RoIStage.train_step, step by step:
+    same host generator -> same sampled RoIs -> same loss, parameter gradients and dL/dfeatures."""
+    from unit_b200.distributed import FlatGradBucket
+    from unit_b200.stage import RoIStage
+    from unit_b200.structures import Boxes, Instances
+
+    def make(seed_gen):
+        cfg, head = _build("voc_split1_ft.yaml", 64, registry)
+        g = seeded(321)
+        with torch.no_grad():
+            for name, p in sorted(head.named_parameters()):
+                if "embeddings" not in name:
+                    p.copy_(torch.randn(p.shape, generator=g) * (0.02 if "bbox" in name else 0.1))
+        head = head.cuda().train()
+        head.sampling_generator = seeded(seed_gen)
+        bucket = FlatGradBucket([p for p in head.parameters() if p.requires_grad])
+
+        def box_head_fn(pooled):
+            m = pooled.mean(dim=[2, 3])
+            return (torch.relu(head.box_head.proj(m)), torch.relu(head.weak_box_head.proj(m)).detach())
+
+        return head, bucket, RoIStage(head, box_head_fn, bucket)
+
+    g = seeded(77)
+    img = (400, 672)
+    feats = torch.randn(2, 64, 25, 42, generator=g).cuda()
+    props, targets = [], []
+    for i in range(2):
+        gt = random_boxes(3, img[0], img[1], g, 48.0)
+        pb = random_boxes(700, img[0], img[1], g, 16.0)
+        pb[:60] = gt[torch.randint(0, 3, (60,), generator=g)] * (1 + 0.06 * (torch.rand(60, 4, generator=g) - 0.5))
+        props.append(Instances(img, proposal_boxes=Boxes(pb.cuda()), objectness_logits=torch.zeros(700, device="cuda")))
+        targets.append(Instances(img, gt_boxes=Boxes(gt.cuda()), gt_classes=torch.randint(0, 20, (3,), generator=g).cuda()))
+    gp = torch.randn(2 * 512, 64, 14, 14, generator=g).cuda()
+    _, b_e, st_e = make(5)
+    _, b_g, st_g = make(5)
+    for step in range(4):
+        le, ge = st_e.train_step(feats, props, targets, grad_pooled_fn=lambda p: gp[:p.shape[0]])
+        lg, gg = st_g.train_step_graphed(feats, props, targets, grad_pooled_fn=lambda p: gp[:p.shape[0]])
+        assert torch.equal(le, lg), (step, le.item(), lg.item())
+        assert torch.equal(b_e.flat, b_g.flat), step
+        assert_close_rms(gg.cpu(), ge.cpu(), 1e-5, "dL/dfeatures (graph vs eager)")  # atomics: order may differ
+    assert st_g.graph_launches > 0 and len(st_g._graphs) == 1
+
+
 def test_mask_head_inference_coco(registry):
     from unit_b200.structures import Boxes, Instances
 

@@ -137,50 +137,49 @@ def add_ground_truth_to_proposals(gt_boxes: List[Boxes], proposals: List[Instanc
     return out
 
 
-def label_and_sample(proposals: List[Instances], targets: List[Instances], *, num_classes: int,
-                     batch_size_per_image: int, positive_fraction: float, thresholds: Sequence[float],
-                     labels: Sequence[int], sample: bool = True, generator: Optional[torch.Generator] = None,
-                     want_vals: bool = False):
-    """Batched core of [D2] ``ROIHeads.label_and_sample_proposals`` (roi_heads.py:459,563,794,925) and of
-    weak_detector_fast_rcnn.py:320-351 (``sample=False``: keep every proposal).
+class LabelMatch:
+    """Device-side result of the label phase (fused IoU+match, label+compaction) for a batch of images."""
 
-    All images go through three launches (fused IoU+match, label+compaction, gather) and ONE device->host read
-    (the fg/bg counts the host needs to draw the reference's randperm(#pos), randperm(#neg)).
-    Returns (proposals_with_gt, matched_idxs per image, matched_vals per image or None).
-    """
+    __slots__ = ("prop_counts", "gt_counts", "prop_boxes", "gt_boxes", "gt_classes", "po", "go", "matches", "mlabels",
+                 "vals", "prop_classes", "pos_idx", "neg_idx", "counts")
+
+
+def label_match(proposals: List[Instances], targets: List[Instances], *, num_classes: int,
+                thresholds: Sequence[float], labels: Sequence[int]) -> LabelMatch:
+    """Phase 1 of ``label_and_sample``: two launches, no host synchronisation (capturable in a CUDA graph)."""
     dev = proposals[0].proposal_boxes.device
-    n_img = len(proposals)
-    prop_counts = [len(p) for p in proposals]
-    gt_counts = [len(t) for t in targets]
-    prop_boxes = cat([p.proposal_boxes.tensor for p in proposals])
-    gt_boxes = cat([t.gt_boxes.tensor for t in targets])
-    gt_classes = cat([t.gt_classes for t in targets]).to(torch.int64)
-    po = ops.offsets_from_counts(prop_counts, dev)
-    go = ops.offsets_from_counts(gt_counts, dev)
-    matches, mlabels, vals = ops.iou_match(gt_boxes, go, prop_boxes, po, thresholds, labels, want_vals=True)
-    prop_classes, pos_idx, neg_idx, counts = ops.label_proposals(matches, mlabels, gt_classes, go, po, num_classes)
+    lm = LabelMatch()
+    lm.prop_counts = [len(p) for p in proposals]
+    lm.gt_counts = [len(t) for t in targets]
+    lm.prop_boxes = cat([p.proposal_boxes.tensor for p in proposals])
+    lm.gt_boxes = cat([t.gt_boxes.tensor for t in targets])
+    lm.gt_classes = cat([t.gt_classes for t in targets]).to(torch.int64)
+    lm.po = ops.offsets_from_counts(lm.prop_counts, dev)
+    lm.go = ops.offsets_from_counts(lm.gt_counts, dev)
+    lm.matches, lm.mlabels, lm.vals = ops.iou_match(lm.gt_boxes, lm.go, lm.prop_boxes, lm.po, thresholds, labels,
+                                                    want_vals=True)
+    lm.prop_classes, lm.pos_idx, lm.neg_idx, lm.counts = ops.label_proposals(lm.matches, lm.mlabels, lm.gt_classes,
+                                                                             lm.go, lm.po, num_classes)
+    return lm
 
-    out, matched_list, vals_list = [], [], []
-    if not sample:
-        off = 0
-        for i, (p, t) in enumerate(zip(proposals, targets)):
-            sl = slice(off, off + prop_counts[i])
-            res = Instances(p.image_size, **p.get_fields())
-            res.gt_classes = prop_classes[sl]
-            m = matches[sl]
-            if gt_counts[i] > 0:
-                for name, value in t.get_fields().items():
-                    if name.startswith("gt_") and not res.has(name):
-                        res.set(name, value[m])
-            else:
-                res.gt_boxes = Boxes(prop_boxes.new_zeros((prop_counts[i], 4)))
-            out.append(res)
-            matched_list.append(m)
-            vals_list.append(vals[sl])
-            off += prop_counts[i]
-        return out, matched_list, (vals_list if want_vals else None)
 
-    counts_h = counts.cpu().tolist()  # the one host sync (the reference syncs per image on nonzero())
+class SampleDraw:
+    """Host-side result of the draw phase: the reference's ``randperm(#pos)``, ``randperm(#neg)`` per image, packed as
+    [perm_pos | perm_neg | ppo pno pso nso] (int64).  With ``capacity`` the two permutation regions have that fixed
+    length, so the device copy of the buffer has a static layout (CUDA-graph replay)."""
+
+    __slots__ = ("host", "pso", "nso", "pos_len", "neg_len", "n_img")
+
+    @property
+    def sizes(self) -> List[int]:
+        return [(self.pso[i + 1] - self.pso[i]) + (self.nso[i + 1] - self.nso[i]) for i in range(self.n_img)]
+
+
+def draw_permutations(counts_h: Sequence[Sequence[int]], batch_size_per_image: int, positive_fraction: float,
+                      generator: Optional[torch.Generator] = None, capacity: Optional[int] = None,
+                      out: Optional[torch.Tensor] = None) -> SampleDraw:
+    """Phase 2 ([D2] ``subsample_labels``, sampling.py): same draws, same order (pos then neg, image by image)."""
+    n_img = len(counts_h)
     max_pos = int(batch_size_per_image * positive_fraction)
     perm_pos, perm_neg = [], []
     ppo, pno, pso, nso = [0], [0], [0], [0]
@@ -194,17 +193,36 @@ def label_and_sample(proposals: List[Instances], targets: List[Instances], *, nu
         pno.append(pno[-1] + n_neg_all)
         pso.append(pso[-1] + num_pos)
         nso.append(nso[-1] + num_neg)
+    d = SampleDraw()
+    d.pso, d.nso, d.n_img = pso, nso, n_img
+    offs = torch.tensor(ppo + pno + pso + nso, dtype=torch.int64)
+    if capacity is None:
+        d.pos_len, d.neg_len = ppo[-1], pno[-1]
+        d.host = torch.cat(perm_pos + perm_neg + [offs])
+    else:
+        assert ppo[-1] <= capacity and pno[-1] <= capacity
+        d.pos_len = d.neg_len = capacity
+        d.host = out if out is not None else torch.empty(2 * capacity + offs.numel(), dtype=torch.int64)
+        torch.cat(perm_pos, out=d.host[:ppo[-1]])
+        torch.cat(perm_neg, out=d.host[capacity:capacity + pno[-1]])
+        d.host[2 * capacity:] = offs
+    return d
+
+
+def sample_from_draw(lm: LabelMatch, draw: SampleDraw, devbuf: torch.Tensor, proposals: List[Instances],
+                     targets: List[Instances], want_vals: bool = False):
+    """Phase 3: one gather launch + the Instances the reference's ``label_and_sample_proposals`` returns."""
+    n_img = draw.n_img
+    pso, nso = draw.pso, draw.nso
     S = pso[-1] + nso[-1]
-    host = torch.cat(perm_pos + perm_neg + [torch.tensor(ppo + pno + pso + nso, dtype=torch.int64)])
-    devbuf = host.to(dev, non_blocking=True)
-    n_pp, n_pn = ppo[-1], pno[-1]
-    d_perm_pos, d_perm_neg = devbuf[:n_pp], devbuf[n_pp:n_pp + n_pn]
-    offs = devbuf[n_pp + n_pn:].to(torch.int32)
+    d_perm_pos = devbuf[:draw.pos_len]
+    d_perm_neg = devbuf[draw.pos_len:draw.pos_len + draw.neg_len]
+    offs = devbuf[draw.pos_len + draw.neg_len:].to(torch.int32)
     k = n_img + 1
     sampled, s_boxes, s_classes, s_matched, s_gt = ops.sample_gather(
-        pos_idx, neg_idx, d_perm_pos, offs[:k], d_perm_neg, offs[k:2 * k], offs[2 * k:3 * k], offs[3 * k:4 * k], po,
-        go, S, prop_boxes, prop_classes, matches, gt_boxes)
-
+        lm.pos_idx, lm.neg_idx, d_perm_pos, offs[:k], d_perm_neg, offs[k:2 * k], offs[2 * k:3 * k], offs[3 * k:4 * k],
+        lm.po, lm.go, S, lm.prop_boxes, lm.prop_classes, lm.matches, lm.gt_boxes)
+    out, matched_list, vals_list = [], [], []
     off = 0
     num_fg, num_bg = [], []
     for i, (p, t) in enumerate(zip(proposals, targets)):
@@ -217,7 +235,7 @@ def label_and_sample(proposals: List[Instances], targets: List[Instances], *, nu
             if name != "proposal_boxes":
                 res.set(name, value[idx])
         res.gt_classes = s_classes[sl]
-        if gt_counts[i] > 0:
+        if lm.gt_counts[i] > 0:
             for name, value in t.get_fields().items():
                 if name.startswith("gt_") and not res.has(name):
                     res.set(name, Boxes(s_gt[sl]) if name == "gt_boxes" else value[s_matched[sl]])
@@ -225,7 +243,7 @@ def label_and_sample(proposals: List[Instances], targets: List[Instances], *, nu
             res.gt_boxes = Boxes(s_gt[sl])
         out.append(res)
         matched_list.append(s_matched[sl])
-        vals_list.append(vals[po_slice(prop_counts, i)][idx] if want_vals else None)
+        vals_list.append(lm.vals[po_slice(lm.prop_counts, i)][idx] if want_vals else None)
         num_fg.append(pso[i + 1] - pso[i])
         num_bg.append(nso[i + 1] - nso[i])
         off += n
@@ -233,6 +251,44 @@ def label_and_sample(proposals: List[Instances], targets: List[Instances], *, nu
     storage.put_scalar("roi_head/num_fg_samples", sum(num_fg) / max(len(num_fg), 1))
     storage.put_scalar("roi_head/num_bg_samples", sum(num_bg) / max(len(num_bg), 1))
     return out, matched_list, (vals_list if want_vals else None)
+
+
+def label_and_sample(proposals: List[Instances], targets: List[Instances], *, num_classes: int,
+                     batch_size_per_image: int, positive_fraction: float, thresholds: Sequence[float],
+                     labels: Sequence[int], sample: bool = True, generator: Optional[torch.Generator] = None,
+                     want_vals: bool = False):
+    """Batched core of [D2] ``ROIHeads.label_and_sample_proposals`` (roi_heads.py:459,563,794,925) and of
+    weak_detector_fast_rcnn.py:320-351 (``sample=False``: keep every proposal).
+
+    All images go through three launches (fused IoU+match, label+compaction, gather) and ONE device->host read
+    (the fg/bg counts the host needs to draw the reference's randperm(#pos), randperm(#neg)).
+    Returns (proposals_with_gt, matched_idxs per image, matched_vals per image or None).
+    """
+    lm = label_match(proposals, targets, num_classes=num_classes, thresholds=thresholds, labels=labels)
+    if not sample:
+        out, matched_list, vals_list = [], [], []
+        off = 0
+        for i, (p, t) in enumerate(zip(proposals, targets)):
+            sl = slice(off, off + lm.prop_counts[i])
+            res = Instances(p.image_size, **p.get_fields())
+            res.gt_classes = lm.prop_classes[sl]
+            m = lm.matches[sl]
+            if lm.gt_counts[i] > 0:
+                for name, value in t.get_fields().items():
+                    if name.startswith("gt_") and not res.has(name):
+                        res.set(name, value[m])
+            else:
+                res.gt_boxes = Boxes(lm.prop_boxes.new_zeros((lm.prop_counts[i], 4)))
+            out.append(res)
+            matched_list.append(m)
+            vals_list.append(lm.vals[sl])
+            off += lm.prop_counts[i]
+        return out, matched_list, (vals_list if want_vals else None)
+
+    counts_h = lm.counts.cpu().tolist()  # the one host sync (the reference syncs per image on nonzero())
+    draw = draw_permutations(counts_h, batch_size_per_image, positive_fraction, generator)
+    devbuf = draw.host.to(lm.prop_boxes.device, non_blocking=True)
+    return sample_from_draw(lm, draw, devbuf, proposals, targets, want_vals)
 
 
 def po_slice(counts: Sequence[int], i: int) -> slice:

@@ -58,8 +58,20 @@ def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
     return ws
 
 
+_I32_CACHE = {}
+
+
 def _i32(values: Sequence[int], dev: torch.device) -> torch.Tensor:
-    return torch.tensor(list(values), dtype=torch.int32, device=dev)
+    """Small read-only int32 device array (offsets, class index sets).  Cached by value: repeated shapes cost no
+    host->device copy, and none is issued while a CUDA graph is being captured after a warm-up pass."""
+    key = (tuple(int(v) for v in values), str(dev))
+    t = _I32_CACHE.get(key)
+    if t is None:
+        if len(_I32_CACHE) >= 512:
+            _I32_CACHE.clear()
+        t = torch.tensor(list(key[0]), dtype=torch.int32, device=dev)
+        _I32_CACHE[key] = t
+    return t
 
 
 def offsets_from_counts(counts: Sequence[int], dev: torch.device) -> torch.Tensor:

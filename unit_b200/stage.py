@@ -24,6 +24,8 @@ class RoIStage:
         self.head = head
         self.box_head_fn = box_head_fn
         self.bucket = bucket
+        self._graphs: Dict[tuple, "_StepGraphs"] = {}
+        self.graph_launches = 0  # library kernels executed through graph replays (not visible to unit_launch_count)
 
     # ------------------------------------------------------------------------------------------- inference
     @torch.no_grad()
@@ -49,9 +51,17 @@ class RoIStage:
         Returns (loss tensor, dL/dfeatures)."""
         head = self.head
         head.move_mappings_to_gpu()
+        sampled = head.label_and_sample_proposals(proposals, targets)
+        loss, grad_feat = self._after_sampling(features, sampled, grad_pooled_fn)
+        if self.bucket is not None:
+            self.bucket.all_reduce_mean()
+        return loss, grad_feat
+
+    def _after_sampling(self, features, sampled: List[Instances], grad_pooled_fn):
+        """Everything after the host draw: shapes are fixed by the sample counts, nothing synchronises."""
+        head = self.head
         if self.bucket is not None:
             self.bucket.zero_()
-        sampled = head.label_and_sample_proposals(proposals, targets)
         boxes = [p.proposal_boxes for p in sampled]
         rois = layers.cat([torch.cat((b.tensor.new_full((len(b), 1), float(i)), b.tensor), dim=1)
                            for i, b in enumerate(boxes)])
@@ -69,6 +79,106 @@ class RoIStage:
         if grad_pooled_fn is not None:
             grad_feat = ops.roi_align_backward(grad_pooled_fn(pooled), rois, features.shape, pool.scales[0],
                                                pool.sampling_ratio, pool.aligned, True)
+        return loss.detach(), grad_feat
+
+    # ------------------------------------------------------------------------------------------- CUDA-graph replay
+    def train_step_graphed(self, features: torch.Tensor, proposals: List[Instances], targets: List[Instances],
+                           grad_pooled_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None):
+        """``train_step`` with the launch-bound parts replayed from CUDA graphs.
+
+        The step is cut at its one unavoidable host round trip (the reference's ``subsample_labels`` needs the fg/bg
+        counts on the host to draw ``randperm``): graph A = append GT + fused IoU/match + label; then the count read,
+        the host draw and ONE host->device copy of the permutations into a fixed-layout buffer; graph B = gather ->
+        ROIAlign fwd -> box head -> similarity/transfer -> losses -> backward -> ROIAlign bwd.  Graphs are keyed by the
+        input buffers (the caller must reuse them: same pointers, same shapes) and by the per-image sample counts; a
+        step whose counts differ from the captured ones runs graph A + the eager remainder.  The returned tensors are
+        the graph's static outputs: they are overwritten by the next replay with the same key."""
+        head = self.head
+        head.move_mappings_to_gpu()
+        key = (features.data_ptr(), tuple(features.shape),
+               tuple(p.proposal_boxes.tensor.data_ptr() for p in proposals), tuple(len(p) for p in proposals),
+               tuple(t.gt_boxes.tensor.data_ptr() for t in targets), tuple(len(t) for t in targets),
+               tuple(t.gt_classes.data_ptr() for t in targets))
+        st = self._graphs.get(key)
+        if st is None:
+            st = _StepGraphs(self, features, proposals, targets, grad_pooled_fn)
+            self._graphs[key] = st
+        out = st.run()
         if self.bucket is not None:
             self.bucket.all_reduce_mean()
-        return loss, grad_feat
+        return out
+
+
+class _StepGraphs:
+    """The two captured graphs of one (input buffers, sample counts) key, with their static tensors."""
+
+    def __init__(self, stage: RoIStage, features, proposals, targets, grad_pooled_fn):
+        from . import _lib
+        self.stage, self.features, self.proposals, self.targets = stage, features, proposals, targets
+        self.grad_pooled_fn = grad_pooled_fn
+        head = stage.head
+        self.kw = dict(num_classes=head.num_classes, thresholds=head.proposal_matcher.user_thresholds,
+                       labels=head.proposal_matcher.labels)
+        dev = features.device
+        self.launches = 0  # kernels of libunit_b200.so inside the two graphs (replays do not pass through the ABI)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up outside capture: lazy handles, workspaces, autograd engine
+            lm = self._label()
+            counts_h = lm.counts.cpu().tolist()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.capacity = int(sum(lm.prop_counts))
+        self.host = torch.empty(2 * self.capacity + 4 * (len(proposals) + 1), dtype=torch.int64).pin_memory()
+        self.devbuf = torch.zeros(self.host.numel(), dtype=torch.int64, device=dev)
+        # ---- graph A
+        self.graph_a = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph_a):
+            self.lm = self._label()
+        self.launches += _lib.launch_count() - n0
+        self.graph_a.replay()
+        draw = self._draw(self.lm.counts.cpu().tolist())
+        self.sizes = draw.sizes
+        self.devbuf.copy_(draw.host, non_blocking=True)
+        # ---- graph B (one eager pass first, on the side stream, with this step's draw)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._after_draw(draw)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph_b = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph_b):
+            self.out = self._after_draw(draw)
+        self.launches += _lib.launch_count() - n0
+        self._pending = draw  # the capture call is itself a step: its draw is replayed once by run()
+
+    def _label(self):
+        head = self.stage.head
+        props = self.proposals
+        if head.proposal_append_gt:
+            props = layers.add_ground_truth_to_proposals([t.gt_boxes for t in self.targets], props)
+        self.props_with_gt = props
+        return layers.label_match(props, self.targets, **self.kw)
+
+    def _draw(self, counts_h):
+        head = self.stage.head
+        return layers.draw_permutations(counts_h, head.batch_size_per_image, head.positive_fraction,
+                                        head.sampling_generator, capacity=self.capacity, out=self.host)
+
+    def _after_draw(self, draw):
+        with torch.no_grad():
+            sampled, _, _ = layers.sample_from_draw(self.lm, draw, self.devbuf, self.props_with_gt, self.targets)
+        return self.stage._after_sampling(self.features, sampled, self.grad_pooled_fn)
+
+    def run(self):
+        if self._pending is not None:
+            draw, self._pending = self._pending, None
+        else:
+            self.graph_a.replay()
+            draw = self._draw(self.lm.counts.cpu().tolist())
+            self.devbuf.copy_(draw.host, non_blocking=True)
+        if draw.sizes != self.sizes:  # rare: fewer candidates than the batch size -> different shapes
+            return self._after_draw(draw)
+        self.graph_b.replay()
+        self.stage.graph_launches += self.launches
+        return self.out
