@@ -59,6 +59,7 @@ struct Params {
   float scale;
   int sampling_ratio, aligned;
   int evict_first;  // L2 policy of the grad_out tiles
+  int sweep3;       // use the unrolled sweep for gw == 3 as well
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -392,6 +393,7 @@ roi_align_bwd_cl(const __grid_constant__ CUtensorMap gmap, const Params p) {
         if (adv) {  // last sample whose lower tap is this feature row: the row is complete, sweep it
           if (gw == 1) sweep<1>(xt, vlo, rowp, cstep, gw);
           else if (gw == 2) sweep<2>(xt, vlo, rowp, cstep, gw);
+          else if (gw == 3 && p.sweep3) sweep<3>(xt, vlo, rowp, cstep, gw);
           else sweep<0>(xt, vlo, rowp, cstep, gw);
           rowp += rstep;
         }
@@ -498,6 +500,8 @@ int launch_bwd_cl(const void* gout, const float* rois, void* gfeat, void* ws, in
   {
     const char* e = getenv("UNIT_ROI_BWD_EVICT_FIRST");
     p.evict_first = e ? atoi(e) : 1;
+    const char* e3 = getenv("UNIT_ROI_BWD_SWEEP3");
+    p.sweep3 = e3 ? atoi(e3) : 1;
   }
   const long long total = (long long)N * C * H * W;  // multiple of 64
   const long long n4 = total / 4 + 16;
