@@ -47,10 +47,10 @@ unsigned long long unit_launch_count(void);
  *   feat      [N,C,H,W]  NCHW, dtype f32 or bf16          rois [R,5] fp32 (batch_idx, x1, y1, x2, y2)
  *   out       [R,C,PH,PW] same dtype as feat
  *   rois_sorted != 0: rois are grouped by ascending batch index (what ROIPooler produces); enables the
- *   slab-resident kernels.  workspace: unit_roi_align_workspace_bytes(N, C, H, W, dtype) bytes.
+ *   slab-resident kernels.  workspace: unit_roi_align_workspace_bytes(N, C, H, W, R, dtype) bytes.
  * Backward writes grad_feat [N,C,H,W] completely (no pre-zeroing needed by the caller).
  */
-size_t unit_roi_align_workspace_bytes(int N, int C, int H, int W, int dtype);
+size_t unit_roi_align_workspace_bytes(int N, int C, int H, int W, int R, int dtype);
 int unit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, int C, int H, int W, int R, int PH,
                        int PW, float spatial_scale, int sampling_ratio, int aligned, int dtype, int rois_sorted,
                        void* workspace, size_t workspace_bytes, unit_stream_t stream);

@@ -132,7 +132,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert set(_lib.exported_symbols()) <= declared
     lib = _lib.lib()
     assert lib.unit_version() >= 100
-    assert lib.unit_roi_align_workspace_bytes(4, 8, 4, 4, 0) >= 16
+    assert lib.unit_roi_align_workspace_bytes(4, 8, 4, 4, 16, 0) >= 16
     assert lib.unit_nms_workspace_bytes(2, 1000) > 36 * 2000
 
 

@@ -29,7 +29,7 @@ _SIGNATURES = {
     "unit_version": (c_int, []),
     "unit_last_error": (c_char_p, []),
     "unit_launch_count": (c_ulonglong, []),
-    "unit_roi_align_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "unit_roi_align_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "unit_roi_align_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                                    c_int, c_int, P, c_size_t, P]),
     "unit_roi_align_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,

@@ -104,6 +104,10 @@ __global__ void roi_offsets_kernel(const float* __restrict__ rois, int R, int N,
 bool fwd_slab2_fits(int C, int H, int W, int dtype);
 int launch_fwd_slab2(const void* feat, const float* rois, void* out, int N, int C, int H, int W, int R, float scale,
                      int sr, int aligned, int dtype, const int* img_off, cudaStream_t st);
+bool fwd_band_fits(int C, int H, int W, int dtype);
+size_t fwd_band_workspace_bytes(int R);
+int launch_fwd_band(const void* feat, const float* rois, void* out, void* tabs_ws, int N, int C, int H, int W, int R,
+                    float scale, int sr, int aligned, int dtype, const int* img_off, cudaStream_t st);
 bool bwd_slab2_fits(int C, int H, int W, int dtype);
 size_t bwd_slab2_workspace_bytes(int N, int C, int H, int W, int dtype);
 int launch_bwd_slab2(const void* gout, const float* rois, void* gfeat, void* f32_scratch, int N, int C, int H, int W,
@@ -123,8 +127,10 @@ using namespace unit::roi;
 
 extern "C" {
 
-size_t unit_roi_align_workspace_bytes(int N, int C, int H, int W, int dtype) {
-  return offsets_bytes(N) + bwd_slab2_workspace_bytes(N, C, H, W, dtype) + 256;
+size_t unit_roi_align_workspace_bytes(int N, int C, int H, int W, int R, int dtype) {
+  const size_t fwd = fwd_band_workspace_bytes(R);
+  const size_t bwd = bwd_slab2_workspace_bytes(N, C, H, W, dtype);
+  return offsets_bytes(N) + (fwd > bwd ? fwd : bwd) + 256;
 }
 
 int unit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, int C, int H, int W, int R, int PH,
@@ -135,6 +141,19 @@ int unit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, in
   if (R == 0) return UNIT_OK;
   UNIT_REQUIRE(feat && rois && out, "roi_align_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (rois_sorted && PH == 14 && PW == 14 && N > 0 && fwd_band_fits(C, H, W, dtype) && dtype == UNIT_F32 &&
+      !getenv("UNIT_ROI_FWD_V3")) {  // bf16 I/O: the pair-interleaved kernel below loads its slab faster
+    const size_t need = offsets_bytes(N) + fwd_band_workspace_bytes(R);
+    if (!workspace || workspace_bytes < need) {
+      set_error("roi_align_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+      return UNIT_EWORKSPACE;
+    }
+    UNIT_REQUIRE((((uintptr_t)out) & 15) == 0, "roi_align_fwd: out must be 16-byte aligned");
+    roi_offsets_kernel<<<cdiv(R + 1, 256), 256, 0, st>>>(rois, R, N, (int*)workspace);
+    UNIT_CHECK_LAUNCH("roi_offsets_kernel");
+    return launch_fwd_band(feat, rois, out, (char*)workspace + offsets_bytes(N), N, C, H, W, R, spatial_scale,
+                           sampling_ratio, aligned, dtype, (const int*)workspace, st);
+  }
   if (rois_sorted && PH == 14 && PW == 14 && N > 0 && fwd_slab2_fits(C, H, W, dtype)) {
     if (!workspace || workspace_bytes < offsets_bytes(N)) {
       set_error("roi_align_fwd: workspace too small (%zu < %zu)", workspace_bytes, offsets_bytes(N));

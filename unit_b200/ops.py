@@ -101,7 +101,7 @@ def roi_align_forward(feat: torch.Tensor, rois: torch.Tensor, output_size: Tuple
     out = torch.empty((R, C, ph, pw), dtype=feat.dtype, device=dev)
     if R == 0:
         return out
-    ws_bytes = lib().unit_roi_align_workspace_bytes(N, C, H, W, _lib.UNIT_F32)
+    ws_bytes = lib().unit_roi_align_workspace_bytes(N, C, H, W, R, _lib.UNIT_F32)
     ws = _workspace(dev, ws_bytes)
     check(lib().unit_roi_align_fwd(_ptr(feat), _ptr(rois), _ptr(out), N, C, H, W, R, ph, pw, float(spatial_scale),
                                    int(sampling_ratio), int(bool(aligned)), _dtype_code(feat), int(bool(rois_sorted)),
@@ -117,7 +117,7 @@ def roi_align_backward(grad_out: torch.Tensor, rois: torch.Tensor, input_shape: 
     N, C, H, W = [int(v) for v in input_shape]
     R, _, ph, pw = grad_out.shape
     grad_in = torch.empty((N, C, H, W), dtype=grad_out.dtype, device=dev)
-    ws_bytes = lib().unit_roi_align_workspace_bytes(N, C, H, W, _dtype_code(grad_out))
+    ws_bytes = lib().unit_roi_align_workspace_bytes(N, C, H, W, R, _dtype_code(grad_out))
     ws = _workspace(dev, ws_bytes)
     check(lib().unit_roi_align_bwd(_ptr(grad_out), _ptr(rois), _ptr(grad_in), N, C, H, W, R, ph, pw,
                                    float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
