@@ -382,7 +382,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     torch.backends.cuda.matmul.allow_tf32 = False
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    wl = Workload(device, dtype, rank, use_graph=not args.no_graph)
+    # Nsight Compute serialises and replays every kernel, which is illegal while a stream is capturing: under a
+    # profiler the step runs eagerly (same kernels, one launch each)
+    profiled = any(k in os.environ for k in ("NV_COMPUTE_PROFILER_PERFWORKS_DIR", "CUDA_INJECTION64_PATH",
+                                             "NV_NSIGHT_INJECTION_TRANSPORT_TYPE"))
+    wl = Workload(device, dtype, rank, use_graph=not (args.no_graph or profiled))
 
     def barrier():
         if world > 1:
