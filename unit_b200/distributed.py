@@ -47,16 +47,19 @@ class FlatGradBucket:
     def all_reduce_mean(self, async_op: bool = False):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return None
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        self._avg = dist.get_backend() == "nccl"  # NCCL averages inside the collective; gloo needs sum + divide
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM, async_op=async_op)
         if async_op:
             return work
-        self.flat.div_(dist.get_world_size())
+        if not self._avg:
+            self.flat.div_(dist.get_world_size())
         return None
 
     def finish(self, work) -> None:
         if work is not None:
             work.wait()
-            self.flat.div_(dist.get_world_size())
+            if not self._avg:
+                self.flat.div_(dist.get_world_size())
 
 
 def gather_detections(boxes: torch.Tensor, scores: torch.Tensor, classes: torch.Tensor, counts: torch.Tensor,

@@ -52,13 +52,16 @@ class RoIStage:
         head = self.head
         head.move_mappings_to_gpu()
         sampled = head.label_and_sample_proposals(proposals, targets)
-        loss, grad_feat = self._after_sampling(features, sampled, grad_pooled_fn)
+        loss, rois, pooled = self._forward_backward(features, sampled)
+        work = self.bucket.all_reduce_mean(async_op=True) if self.bucket is not None else None
+        grad_feat = self._roi_backward(features, rois, pooled, grad_pooled_fn)  # overlaps the all-reduce
         if self.bucket is not None:
-            self.bucket.all_reduce_mean()
+            self.bucket.finish(work)
         return loss, grad_feat
 
-    def _after_sampling(self, features, sampled: List[Instances], grad_pooled_fn):
-        """Everything after the host draw: shapes are fixed by the sample counts, nothing synchronises."""
+    def _forward_backward(self, features, sampled: List[Instances]):
+        """Sampled RoIs -> ROIAlign fwd -> box head -> transfer -> losses -> backward into the bucket.  Shapes are
+        fixed by the sample counts and nothing synchronises (capturable)."""
         head = self.head
         if self.bucket is not None:
             self.bucket.zero_()
@@ -75,11 +78,14 @@ class RoIStage:
         losses = head.box_predictor.losses(predictions, sampled)
         loss = losses["loss_cls"] + losses["loss_box_reg"]
         loss.backward()
-        grad_feat = None
-        if grad_pooled_fn is not None:
-            grad_feat = ops.roi_align_backward(grad_pooled_fn(pooled), rois, features.shape, pool.scales[0],
-                                               pool.sampling_ratio, pool.aligned, True)
-        return loss.detach(), grad_feat
+        return loss.detach(), rois, pooled
+
+    def _roi_backward(self, features, rois, pooled, grad_pooled_fn):
+        if grad_pooled_fn is None:
+            return None
+        pool = self.head.box_pooler
+        return ops.roi_align_backward(grad_pooled_fn(pooled), rois, features.shape, pool.scales[0],
+                                      pool.sampling_ratio, pool.aligned, True)
 
     # ------------------------------------------------------------------------------------------- CUDA-graph replay
     def train_step_graphed(self, features: torch.Tensor, proposals: List[Instances], targets: List[Instances],
@@ -89,7 +95,8 @@ class RoIStage:
         The step is cut at its one unavoidable host round trip (the reference's ``subsample_labels`` needs the fg/bg
         counts on the host to draw ``randperm``): graph A = append GT + fused IoU/match + label; then the count read,
         the host draw and ONE host->device copy of the permutations into a fixed-layout buffer; graph B = gather ->
-        ROIAlign fwd -> box head -> similarity/transfer -> losses -> backward -> ROIAlign bwd.  Graphs are keyed by the
+        ROIAlign fwd -> box head -> similarity/transfer -> losses -> backward; graph C = ROIAlign bwd, replayed while
+        the gradient bucket's all-reduce runs on NCCL's stream.  Graphs are keyed by the
         input buffers (the caller must reuse them: same pointers, same shapes) and by the per-image sample counts; a
         step whose counts differ from the captured ones runs graph A + the eager remainder.  The returned tensors are
         the graph's static outputs: they are overwritten by the next replay with the same key."""
@@ -103,10 +110,7 @@ class RoIStage:
         if st is None:
             st = _StepGraphs(self, features, proposals, targets, grad_pooled_fn)
             self._graphs[key] = st
-        out = st.run()
-        if self.bucket is not None:
-            self.bucket.all_reduce_mean()
-        return out
+        return st.run()
 
 
 class _StepGraphs:
@@ -140,15 +144,19 @@ class _StepGraphs:
         draw = self._draw(self.lm.counts.cpu().tolist())
         self.sizes = draw.sizes
         self.devbuf.copy_(draw.host, non_blocking=True)
-        # ---- graph B (one eager pass first, on the side stream, with this step's draw)
+        # ---- graphs B and C (one eager pass first, on the side stream, with this step's draw)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            self._after_draw(draw)
+            _, rois, pooled = self._after_draw(draw)
+            stage._roi_backward(features, rois, pooled, grad_pooled_fn)
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph_b = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph_b):
-            self.out = self._after_draw(draw)
+            self.loss, self.rois, self.pooled = self._after_draw(draw)
+        self.graph_c = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_c, pool=self.graph_b.pool()):
+            self.grad_feat = stage._roi_backward(features, self.rois, self.pooled, grad_pooled_fn)
         self.launches += _lib.launch_count() - n0
         self._pending = draw  # the capture call is itself a step: its draw is replayed once by run()
 
@@ -168,17 +176,29 @@ class _StepGraphs:
     def _after_draw(self, draw):
         with torch.no_grad():
             sampled, _, _ = layers.sample_from_draw(self.lm, draw, self.devbuf, self.props_with_gt, self.targets)
-        return self.stage._after_sampling(self.features, sampled, self.grad_pooled_fn)
+        return self.stage._forward_backward(self.features, sampled)
 
     def run(self):
+        stage = self.stage
         if self._pending is not None:
             draw, self._pending = self._pending, None
         else:
             self.graph_a.replay()
             draw = self._draw(self.lm.counts.cpu().tolist())
             self.devbuf.copy_(draw.host, non_blocking=True)
-        if draw.sizes != self.sizes:  # rare: fewer candidates than the batch size -> different shapes
-            return self._after_draw(draw)
-        self.graph_b.replay()
-        self.stage.graph_launches += self.launches
-        return self.out
+        graphed = draw.sizes == self.sizes  # rare otherwise: fewer candidates than the batch size -> other shapes
+        if graphed:
+            self.graph_b.replay()
+            loss, rois, pooled = self.loss, self.rois, self.pooled
+        else:
+            loss, rois, pooled = self._after_draw(draw)
+        work = stage.bucket.all_reduce_mean(async_op=True) if stage.bucket is not None else None
+        if graphed:
+            self.graph_c.replay()
+            grad_feat = self.grad_feat
+            stage.graph_launches += self.launches
+        else:
+            grad_feat = stage._roi_backward(self.features, rois, pooled, self.grad_pooled_fn)
+        if stage.bucket is not None:
+            stage.bucket.finish(work)
+        return loss, grad_feat
