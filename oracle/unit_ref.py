@@ -58,11 +58,20 @@ def visual_similarity(probs: torch.Tensor, base: torch.Tensor, threshold: float)
     return v
 
 
+def _first_k(terms: List[str], tag: str) -> int:
+    """roi_heads.py:274,285,296,307: ``int([x for x in terms if tag in x][0].split("-")[1])`` (substring match)."""
+    return int([x for x in terms if tag in x][0].split("-")[1])
+
+
 def similarity_matrices(lingual: Optional[torch.Tensor], visual: Optional[torch.Tensor],
-                        terms: Dict[str, List[str]], n_novel: int, n_base: int, combination: str = "Sum"):
-    """roi_heads.py:266-336 restricted to the {'lingual','visual','Average','None'} terms (the TopK/WTopK/LSDA/VisualK
-    branches at :273-315 need the OICR weights)."""
-    dev = (visual if visual is not None else lingual).device
+                        terms: Dict[str, List[str]], n_novel: int, n_base: int, combination: str = "Sum",
+                        class_weights: Optional[torch.Tensor] = None, mean_logits: Optional[torch.Tensor] = None,
+                        base: Optional[torch.Tensor] = None, novel: Optional[torch.Tensor] = None,
+                        num_classes: Optional[int] = None):
+    """roi_heads.py:266-336, every term.  ``class_weights`` = mean of the OICR predictor weights [K+1,D] (TopK / WTopK
+    / LSDA, :275,286,297), ``mean_logits`` = mean OICR logits of the RoIs [R,K+1] (VisualK, :308).  The reference tests
+    ``'TopK' in x`` by SUBSTRING, so a ``WTopK-k`` term also switches the ``TopK`` branch on; reproduced."""
+    dev = (visual if visual is not None else (lingual if lingual is not None else class_weights)).device
     similarity = {}
     for head_type, tl in terms.items():
         s = torch.zeros(n_novel, n_base, device=dev)
@@ -70,8 +79,35 @@ def similarity_matrices(lingual: Optional[torch.Tensor], visual: Optional[torch.
             weight = 1.0 / len(tl) if len(tl) else 0.0
             if "lingual" in tl:
                 s = s + weight * torch.softmax(lingual, dim=-1)
+            if any("TopK" in x for x in tl):
+                k = _first_k(tl, "TopK")
+                ws = torch.mm(class_weights.index_select(0, novel), class_weights.index_select(0, base).t())
+                _, idx = torch.topk(ws, k, dim=-1)
+                t = torch.zeros(n_novel, n_base, device=dev).scatter(1, idx, 1.0)
+                s = s + weight * (t / torch.sum(t, dim=-1, keepdim=True))
+            if any("WTopK" in x for x in tl):
+                k = _first_k(tl, "WTopK")
+                ws = torch.mm(class_weights.index_select(0, novel), class_weights.index_select(0, base).t())
+                top, idx = torch.topk(ws, k, dim=-1)
+                t = torch.zeros(n_novel, n_base, device=dev).scatter(1, idx, top)
+                s = s + weight * (t / torch.sum(t, dim=-1, keepdim=True))
+            if any("LSDA" in x for x in tl):
+                k = _first_k(tl, "LSDA")
+                ws = torch.norm(class_weights.index_select(0, novel).unsqueeze(1) -
+                                class_weights.index_select(0, base).unsqueeze(0), dim=-1)
+                _, idx = torch.topk(ws, k, dim=-1, largest=False)
+                t = torch.zeros(n_novel, n_base, device=dev).scatter(1, idx, 1.0)
+                s = s + weight * (t / torch.sum(t, dim=-1, keepdim=True))
+            if any("VisualK" in x for x in tl):
+                k = _first_k(tl, "VisualK")
+                cw = torch.softmax(mean_logits.narrow(1, 0, num_classes), -1).index_select(1, base)
+                ws = cw / torch.sum(cw, -1, keepdim=True).clamp(min=1e-9)
+                top, idx = torch.topk(ws, k, dim=-1)
+                t = torch.zeros(ws.size(0), n_base, device=dev).scatter(1, idx, top)
+                t = t / torch.sum(t, dim=-1, keepdim=True)
+                s = s.unsqueeze(0) + weight * t.unsqueeze(1)
             if "visual" in tl:
-                s = s.unsqueeze(0) + weight * visual.unsqueeze(1)
+                s = s.unsqueeze(0) + weight * visual.unsqueeze(1)  # 4-D after VisualK, as in the reference
             if "Average" in tl:
                 s = s.fill_(1.0)
                 s = s / torch.sum(s, dim=-1, keepdim=True)

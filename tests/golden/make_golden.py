@@ -101,8 +101,8 @@ def _predictor_case(ns, yaml_rel, seed, R, overrides=()):
     return cfg, head, x, xw
 
 
-def make_predictor(ns, tag, yaml_rel, seed, R, training):
-    cfg, head, x, xw = _predictor_case(ns, yaml_rel, seed, R)
+def make_predictor(ns, tag, yaml_rel, seed, R, training, overrides=()):
+    cfg, head, x, xw = _predictor_case(ns, yaml_rel, seed, R, overrides)
     head.train(training)
     pred = head.box_predictor
     head.move_mappings_to_gpu() if False else None
@@ -243,11 +243,19 @@ def main():
         "predictor_voc_ft_eval.pt": make_predictor(ns, "voc", "VOC/FT/10_shot/VOC-RCNN-101-C4-split1-ft.yaml", 14,
                                                    24, False),
         "predictor_coco_ft_eval.pt": make_predictor(ns, "coco", "COCO/COCO-RCNN-50-C4-split1-ft.yaml", 15, 8, False),
+        # non-default similarity terms (roi_heads.py:273-315), reachable through FINETUNE_TERMS overrides
+        "predictor_voc_ft_terms.pt": make_predictor(
+            ns, "voc", "VOC/FT/10_shot/VOC-RCNN-101-C4-split1-ft.yaml", 16, 24, False,
+            ["MODEL.ROI_HEADS.FINETUNE_TERMS.CLASSIFIER", ["lingual", "WTopK-3", "visual"],
+             "MODEL.ROI_HEADS.FINETUNE_TERMS.BBOX", ["LSDA-2", "VisualK-4"]]),
         "head_voc.pt": make_head_voc(ns),
         "mask_head.pt": make_mask_head(ns),
         "weak_label.pt": make_weak_label(ns),
     }
+    only = set(sys.argv[1:])  # optional: regenerate just the named fixtures
     for name, obj in fixtures.items():
+        if only and name not in only:
+            continue
         path = os.path.join(HERE, name)
         torch.save(obj, path)
         print(f"{name:32s} {os.path.getsize(path) / 1024:8.1f} KiB")

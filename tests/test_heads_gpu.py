@@ -85,6 +85,67 @@ def test_head_matches_reference_verbatim_fixture(registry):
         assert_close_rms(inst.pred_boxes.tensor.cpu(), gold["det_boxes"][i], 1e-5, "det boxes")
 
 
+def test_nondefault_similarity_terms_match_reference_fixture(registry):
+    """FINETUNE_TERMS.CLASSIFIER = [lingual, WTopK-3, visual], BBOX = [LSDA-2, VisualK-4] (roi_heads.py:273-315):
+    similarity matrices, transferred scores and box deltas vs the reference run verbatim (committed fixture)."""
+    gold = load_golden("predictor_voc_ft_terms.pt")
+    old = _StandInBoxHead.OUT
+    _StandInBoxHead.OUT = gold["x"].shape[1]
+    try:
+        cfg, head = _build("voc_split1_ft.yaml", 8, registry,
+                           ["MODEL.ROI_HEADS.FINETUNE_TERMS.CLASSIFIER", ["lingual", "WTopK-3", "visual"],
+                            "MODEL.ROI_HEADS.FINETUNE_TERMS.BBOX", ["LSDA-2", "VisualK-4"]])
+    finally:
+        _StandInBoxHead.OUT = old
+    sd = dict(gold["weights"])
+    sd["embeddings.weight"] = load_golden("glove_mean.pt")["embeddings"]
+    missing, unexpected = head.box_predictor.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    head = head.cuda().eval()
+    head.move_mappings_to_gpu()
+    x, xw = gold["x"].cuda(), gold["x_weak_branch"].cuda()
+    with torch.no_grad():
+        sim = head.get_similarity_matrices(x)
+        mat = sim.materialize()
+        (scores, bbox), _ = head.box_predictor(x, supervised_branch_x_weak=xw,
+                                               novel_classes=head._novel_classes_tensor,
+                                               base_classes=head._base_classes_tensor, similarity=sim)
+    for h in ("cls", "bbox"):
+        assert mat[h].shape == gold["similarity"][h].shape
+        assert (mat[h].cpu() - gold["similarity"][h]).abs().max() <= 1e-5, h
+    assert_close_rms(scores.cpu(), gold["scores"], 2e-5, "scores (non-default terms)")
+    assert_close_rms(bbox.cpu(), gold["bbox"], 2e-5, "bbox (non-default terms)")
+
+
+def test_tta_aggregation_matches_oracle(registry):
+    """rcnn.py:495-527: scores summed and deltas averaged over augmentations, then decode + fast_rcnn_inference."""
+    from oracle.d2.ops import Box2BoxTransform, fast_rcnn_inference as ref_inference
+    from unit_b200.structures import Boxes, Instances
+
+    cfg, head = _build("voc_split1_ft.yaml", 8, registry)
+    head = head.cuda().eval()
+    g = seeded(99)
+    R, K = 300, 20
+    boxes = random_boxes(R, 800, 1333, g, 16.0)
+    props = [Instances((800, 1333), proposal_boxes=Boxes(boxes.cuda()), objectness_logits=torch.zeros(R, device="cuda"))]
+    outs = []
+    for _ in range(3):  # three augmentations: per-augmentation probabilities and deltas
+        probs = torch.softmax(3.0 * torch.randn(R, K + 1, generator=g), -1)
+        deltas = 0.3 * torch.randn(R, 4 * K, generator=g)
+        outs.append([probs, deltas])
+    insts, kept = head.box_predictor.inference_tta([[p.cuda(), d.cuda()] for p, d in outs], props)
+    scores = torch.stack([o[0] for o in outs]).sum(0)
+    deltas = torch.stack([o[1] for o in outs]).mean(0)
+    pred_boxes = Box2BoxTransform((10.0, 10.0, 5.0, 5.0)).apply_deltas(deltas, boxes)
+    pred = head.box_predictor
+    ref, ref_kept = ref_inference((pred_boxes,), (scores,), [(800, 1333)], pred.test_score_thresh, pred.test_nms_thresh,
+                                  pred.test_topk_per_image)
+    assert torch.equal(kept[0].cpu(), ref_kept[0])
+    assert torch.equal(insts[0].pred_classes.cpu(), ref[0].pred_classes)
+    assert_close_rms(insts[0].scores.cpu(), ref[0].scores, 1e-6, "tta scores")
+    assert_close_rms(insts[0].pred_boxes.tensor.cpu(), ref[0].pred_boxes.tensor, 1e-5, "tta boxes")
+
+
 def _oracle_inference(head, x, xw, props_cpu, sizes, K, kind):
     """oracle.unit_ref on CPU with the head's weights."""
     from oracle import unit_ref

@@ -83,6 +83,29 @@ def test_unit_ref_against_reference_fixture(name):
         assert torch.allclose(insts[0].scores, gold["det_scores"], rtol=1e-5, atol=1e-7)
 
 
+def test_unit_ref_nondefault_similarity_terms_fixture():
+    """TopK / WTopK / LSDA / VisualK (roi_heads.py:273-315) against the reference run verbatim with
+    FINETUNE_TERMS.CLASSIFIER = [lingual, WTopK-3, visual], BBOX = [LSDA-2, VisualK-4]."""
+    gold = load_golden("predictor_voc_ft_terms.pt")
+    emb = load_golden("glove_mean.pt")["embeddings"]
+    w = dict(gold["weights"])
+    base, novel, K = gold["base"], gold["novel"], gold["num_classes"]
+    assert gold["terms"]["cls"] == ["lingual", "WTopK-3", "visual"] and gold["terms"]["bbox"] == ["LSDA-2", "VisualK-4"]
+    logits = unit_ref.oicr_mean_logits(gold["x"], w)
+    L = unit_ref.lingual_similarity(emb, gold["indexer"], base, novel)
+    V = unit_ref.visual_similarity(logits, base, gold["threshold"])
+    cw = torch.stack([w[f"weak_detector_head.oicr_predictors.{k}.weight"] for k in range(3)]).mean(0)
+    sim = unit_ref.similarity_matrices(L, V, gold["terms"], len(novel), len(base), class_weights=cw,
+                                       mean_logits=logits, base=base, novel=novel, num_classes=K)
+    for h in ("cls", "bbox"):
+        assert sim[h].shape == gold["similarity"][h].shape
+        assert torch.allclose(sim[h], gold["similarity"][h], rtol=1e-5, atol=1e-6)
+    scores, bbox = unit_ref.predictor_forward(gold["x"], gold["x_weak_branch"], w, sim, base, novel, K,
+                                              kind="FineTune", training=False)
+    assert torch.allclose(scores, gold["scores"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(bbox, gold["bbox"], rtol=1e-5, atol=1e-6)
+
+
 def test_mask_transfer_fixture():
     gold = load_golden("mask_head.pt")
     full = unit_ref.mask_transfer(gold["logits_fixed"], gold["similarity_seg"], gold["base"], gold["novel"],

@@ -401,6 +401,15 @@ class TransferSpec:
         self.norm = dict(norm or {})
         self.vis_threshold = float(vis_threshold)
         self.static_per_roi = int(static_per_roi)
+        self.wk = {}
+
+    def with_static(self, static: dict, static_per_roi: int) -> "TransferSpec":
+        """Same class sets and term weights with other static blocks (per-RoI terms: bit h of ``static_per_roi``)."""
+        import copy
+        other = copy.copy(self)
+        other.static = {k: (None if v is None else _c(v, _F32)) for k, v in static.items()}
+        other.static_per_roi = int(static_per_roi)
+        return other
 
     def params(self, R: int, do_transfer: bool, novel_neg_inf: bool) -> TransferParams:
         g = lambda d, k, default: d.get(k, default)

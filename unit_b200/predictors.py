@@ -391,6 +391,17 @@ class SupervisedDetectorOutputsBase(nn.Module):
                                    self.test_score_thresh, self.test_nms_thresh, self.test_topk_per_image)
 
 
+    def inference_tta(self, tta_predictions, proposals):
+        """Test-time-augmentation aggregation of the meta-architecture (rcnn.py:495-527): the per-augmentation
+        ``[probs, deltas]`` returned by ``inference(..., tta=True)`` are reduced -- class probabilities SUMMED, box deltas
+        AVERAGED -- then decoded on the un-augmented proposals and sent through ``fast_rcnn_inference``."""
+        scores = torch.stack([p[0] for p in tta_predictions]).sum(0)
+        deltas = torch.stack([p[1] for p in tta_predictions]).mean(0)
+        n = [len(p) for p in proposals]
+        boxes = self.predict_boxes([scores, deltas], proposals)
+        return fast_rcnn_inference(boxes, scores.split(n), [x.image_size for x in proposals],
+                                   self.test_score_thresh, self.test_nms_thresh, self.test_topk_per_image)
+
 @FAST_RCNN_REGISTRY.register()
 class SupervisedDetectorOutputsFineTune(SupervisedDetectorOutputsBase):
     """fast_rcnn.py:470-533: adds zero-initialised ``cls_score_ft`` / ``bbox_pred_ft``; transfer applied in

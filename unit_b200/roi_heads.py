@@ -236,10 +236,43 @@ class WSROIHead(StandardROIHeads):
             self._novel_classes_tensor = self._novel_classes_tensor.to(device)
 
     # -- similarity ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _term_k(tl, tag: str) -> int:
+        """roi_heads.py:274,285,296,307: k of the first term CONTAINING ``tag`` (the reference matches by substring, so
+        ``WTopK-k`` also switches the ``TopK`` branch on)."""
+        return int([t for t in tl if tag in t][0].split("-")[1])
+
+    def _weight_terms(self, tl, device) -> torch.Tensor:
+        """TopK / WTopK / LSDA (roi_heads.py:273-305): class-level [Nn,B] terms from the mean OICR predictor weights,
+        unweighted sum (every term has the same 1/len(terms) weight).  A handful of tiny ATen ops, once per model."""
+        cw = self.box_predictor.weak_detector_head.mean_oicr_weight()[0].detach().to(device)
+        base_w = cw.index_select(0, self._base_classes_tensor)
+        novel_w = cw.index_select(0, self._novel_classes_tensor)
+        Nn, B = novel_w.shape[0], base_w.shape[0]
+        out = torch.zeros(Nn, B, device=device)
+        if any("TopK" in t for t in tl):
+            _, idx = torch.topk(novel_w @ base_w.t(), self._term_k(tl, "TopK"), dim=-1)
+            t = torch.zeros(Nn, B, device=device).scatter(1, idx, 1.0)
+            out = out + t / t.sum(-1, keepdim=True)
+        if any("WTopK" in t for t in tl):
+            top, idx = torch.topk(novel_w @ base_w.t(), self._term_k(tl, "WTopK"), dim=-1)
+            t = torch.zeros(Nn, B, device=device).scatter(1, idx, top)
+            out = out + t / t.sum(-1, keepdim=True)
+        if any("LSDA" in t for t in tl):
+            dist = torch.norm(novel_w.unsqueeze(1) - base_w.unsqueeze(0), dim=-1)
+            _, idx = torch.topk(dist, self._term_k(tl, "LSDA"), dim=-1, largest=False)
+            t = torch.zeros(Nn, B, device=device).scatter(1, idx, 1.0)
+            out = out + t / t.sum(-1, keepdim=True)
+        return out
+
     def _transfer_spec(self, device) -> ops.TransferSpec:
         """Class-level part of ``get_similarity_matrices`` (roi_heads.py:266-334), reduced once per model/device:
-        static[h] = sum of the class-level terms x their 1/len(terms) weight, wv[h] = weight of 'visual'."""
+        static[h] = sum of the class-level terms x their 1/len(terms) weight, wv[h] = weight of 'visual',
+        ``spec.wk[h]`` = (weight, k) of a 'VisualK-k' term (added per RoI in ``get_similarity_matrices``)."""
+        weight_terms = any(("TopK" in t) or ("LSDA" in t) for tl in self.terms.values() for t in tl)
         key = str(device)
+        if weight_terms:  # TopK / WTopK / LSDA read the OICR weights: rebuild when they change (base training)
+            key = (key,) + tuple(l.weight._version for l in self.box_predictor.weak_detector_head.oicr_predictors)
         if key in self._spec_cache:
             return self._spec_cache[key]
         self.move_mappings_to_gpu()
@@ -248,26 +281,31 @@ class WSROIHead(StandardROIHeads):
         if self.compute_similarity["lingual"]:
             _, soft = ops.lingual_similarity(self.box_predictor.embeddings.weight, self._coco_indexer_tensor,
                                              self._base_classes_tensor, self._novel_classes_tensor)
-        static, wv, norm = {}, {}, {}
+        static, wv, norm, wk = {}, {}, {}, {}
         for head, tl in self.terms.items():
             tl = list(tl)
-            unsupported = [t for t in tl if t not in ("lingual", "visual", "Average", "None")]
-            if unsupported:
-                raise NotImplementedError(f"similarity terms {unsupported} are SURVEY.md section 8f rank-1 "
-                                          "follow-ups (TopK/WTopK/LSDA/VisualK)")
             if self.similarity_combination == "Sum":
                 w = 1.0 / len(tl) if len(tl) else 0.0
                 st = torch.zeros(Nn, B, device=device)
                 if "lingual" in tl:
                     st = st + w * soft
+                if any(("TopK" in t) or ("LSDA" in t) for t in tl):
+                    st = st + w * self._weight_terms(tl, device)
                 wv[head] = w if "visual" in tl else 0.0
+                if any("VisualK" in t for t in tl):
+                    if "visual" in tl:
+                        raise ValueError("'VisualK-k' together with 'visual' makes the reference build a 4-D similarity "
+                                         "(roi_heads.py:315-317) that its own transfer (fast_rcnn.py:407) rejects")
+                    wk[head] = (w, self._term_k(tl, "VisualK"))
                 if "Average" in tl:  # fill_(1.) overrides every other term (roi_heads.py:319-321)
                     st = torch.full((Nn, B), 1.0 / B, device=device)
                     wv[head] = 0.0
+                    wk.pop(head, None)
                 if len(tl) > 0 and "None" not in tl:
                     norm[head] = 1
                 else:  # 0.0 * similarity (roi_heads.py:324-325)
                     st, wv[head], norm[head] = torch.zeros(Nn, B, device=device), 0.0, 0
+                    wk.pop(head, None)
                 static[head] = st
             else:
                 # product mode starts from zeros (roi_heads.py:268,327-332): softmax(0) = uniform when any term
@@ -275,18 +313,38 @@ class WSROIHead(StandardROIHeads):
                 wv[head], norm[head] = 0.0, 0
         spec = ops.TransferSpec(self.num_classes, self._base_classes_id, self._novel_classes_id, device, static, wv,
                                 norm, self.visual_threshold)
+        spec.wk = wk
+        if len(self._spec_cache) > 8:
+            self._spec_cache.clear()
         self._spec_cache[key] = spec
         return spec
+
+    def _visualk_spec(self, spec: ops.TransferSpec, logits: torch.Tensor) -> ops.TransferSpec:
+        """'VisualK-k' (roi_heads.py:306-315): per-RoI top-k of the renormalised base-class probabilities (softmax over
+        the K foreground logits), added to the class-level terms as a per-RoI static [R,Nn,B] block."""
+        static, per_roi = dict(spec.static), spec.static_per_roi
+        order = {"cls": 0, "bbox": 1, "seg": 2}
+        for head, (w, k) in spec.wk.items():
+            cw = torch.softmax(logits.narrow(1, 0, self.num_classes), -1).index_select(1, self._base_classes_tensor)
+            ws = cw / cw.sum(-1, keepdim=True).clamp(min=1e-9)
+            top, idx = torch.topk(ws, k, dim=-1)
+            t = torch.zeros_like(ws).scatter(1, idx, top)
+            t = t / t.sum(-1, keepdim=True)
+            static[head] = (static[head].unsqueeze(0) + w * t.unsqueeze(1)).contiguous()
+            per_roi |= 1 << order[head]
+        return spec.with_static(static, per_roi)
 
     def get_similarity_matrices(self, box_features: torch.Tensor, return_similarity: bool = False):
         """roi_heads.py:245-336.  Returns a :class:`FusedSimilarity`; ``.materialize()`` gives the explicit
         ``{'cls','bbox'[,'seg']: [R,Nn,B]}`` dict of the reference."""
         spec = self._transfer_spec(box_features.device)
         vis_logits = None
-        if self.compute_similarity["visual"]:
+        if self.compute_similarity["visual"] or spec.wk:
             feats = box_features.mean(dim=[2, 3]) if box_features.dim() > 2 else box_features
             with torch.no_grad():
                 vis_logits = self.box_predictor.weak_detector_head.mean_logits(feats)
+                if spec.wk:
+                    spec = self._visualk_spec(spec, vis_logits)
         sim = FusedSimilarity(spec, vis_logits, tuple(self.terms.keys()))
         if return_similarity:
             raw, _ = ops.lingual_similarity(self.box_predictor.embeddings.weight, self._coco_indexer_tensor,

@@ -40,6 +40,25 @@ class RoIStage:
                                             base_classes=head._base_classes_tensor, similarity=sim)
         return head.box_predictor.inference(predictions, proposals)
 
+    @torch.no_grad()
+    def infer_tta(self, features: Sequence[torch.Tensor], aug_proposals: Sequence[List[Instances]],
+                  proposals: List[Instances]):
+        """rcnn.py:495-527: one pass per augmentation (its own feature map and transformed proposals, same RoI order)
+        with ``tta=True``, then ``inference_tta`` on the un-augmented ``proposals``."""
+        head = self.head
+        head.move_mappings_to_gpu()
+        outs = []
+        for feats, props in zip(features, aug_proposals):
+            pooled = head.box_pooler([feats], [p.proposal_boxes for p in props])
+            x, xw = self.box_head_fn(pooled)
+            sim = head.get_similarity_matrices(x)
+            predictions, _ = head.box_predictor(x, supervised_branch_x_weak=xw,
+                                                novel_classes=head._novel_classes_tensor,
+                                                base_classes=head._base_classes_tensor, similarity=sim)
+            res, _ = head.box_predictor.inference(predictions, props, tta=True)
+            outs.append(res)
+        return head.box_predictor.inference_tta(outs, proposals)
+
     # ------------------------------------------------------------------------------------------- fine-tune step
     def train_step(self, features: torch.Tensor, proposals: List[Instances], targets: List[Instances],
                    grad_pooled_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None):
