@@ -442,9 +442,15 @@ def run_ours(args):
         peak, peak_src = measured_peak_gbs()
         dom = max(kernel_ms, key=kernel_ms.get)
         achieved = alg_bytes / (kernel_ms[dom] * 1e-3) / 1e9
+        traffic = None
+        try:  # measured DRAM bytes per launch of that kernel (ncu --set full, see profiles/)
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                traffic = int(json.load(f)[dom]["dram_bytes"]) if dtype == torch.float32 else None
+        except Exception:
+            traffic = None
         roofline = {
             "kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes,
             "per_kernel": {k: {"ms": v, "GBps": alg_bytes / (v * 1e-3) / 1e9, "frac": alg_bytes / (v * 1e-3) / 1e9 / peak}
                            for k, v in kernel_ms.items()},

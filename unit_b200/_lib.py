@@ -9,7 +9,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libunit_b200.so")
+LIB_PATH = os.environ.get("UNIT_B200_LIB") or os.path.join(_HERE, "libunit_b200.so")  # override: kernel-variant experiments
 
 UNIT_F32, UNIT_BF16 = 0, 1
 

@@ -34,8 +34,14 @@ constexpr int CB = 64;                   // channels per work item (two per lane
 constexpr int CHUNK_ROWS = 2;            // bin rows per TMA tile
 constexpr int CHUNK_F = CHUNK_ROWS * P;  // 28 floats per channel and tile
 constexpr int NCHUNK = P / CHUNK_ROWS;   // 7
-constexpr int NST = 2;                   // tile buffers per warp
-constexpr int NW = 12;
+#ifndef UNIT_BWD_NST
+#define UNIT_BWD_NST 2
+#endif
+#ifndef UNIT_BWD_NW
+#define UNIT_BWD_NW 12
+#endif
+constexpr int NST = UNIT_BWD_NST;        // tile buffers per warp
+constexpr int NW = UNIT_BWD_NW;
 constexpr int NT = NW * 32;
 constexpr int MAXG = 6;                  // sampling grid with tables: RoI side <= 84 feature cells (1344 px at 1/16)
 constexpr int MAXS = P * MAXG;
@@ -128,7 +134,9 @@ __device__ __forceinline__ void sweep_step(float2& c0, float2& c1, char*& cell, 
       "and.b32 fl, fl, 1;\n"
       "setp.eq.u32 q, fl, 0;\n"
       "@q bra.uni SWEEP_NEXT;\n"
+#ifndef UNIT_BWD_NORED
       "red.global.add.v2.f32 [%4], {%0, %1};\n"
+#endif
       "add.s64 %4, %4, %11;\n"
       "mov.f32 %0, %2;\n"
       "mov.f32 %1, %3;\n"
@@ -278,7 +286,11 @@ __device__ __forceinline__ void sweep(const float4* __restrict__ xt, const f2 (&
       for (int ix = 0; ix < gw; ++ix) sweep_step(c0, c1, cell, *xt++, vv, cstep);
     }
   }
+#ifndef UNIT_BWD_NORED
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(cell), "f"(c0.x), "f"(c0.y));  // upper-tap-only column
+#else
+  asm volatile("" ::"l"(cell), "f"(c0.x), "f"(c0.y));
+#endif
 }
 
 __global__ void __launch_bounds__(NT, 1)
@@ -307,7 +319,11 @@ roi_align_bwd_cl(const __grid_constant__ CUtensorMap gmap, const Params p) {
     const int r = (int)(it / nblk);
     const int cb = (int)(it - (long long)r * nblk);
     mbar_expect_tx(&wa->bar[b], TILE_BYTES);
+#ifdef UNIT_BWD_SAMETILE  // timing experiment: every tile comes from the same (L2-resident) place
+    tma_tile_load(wa->stage[b], &gmap, &wa->bar[b], 0, (r & 7) * CB, policy);
+#else
     tma_tile_load(wa->stage[b], &gmap, &wa->bar[b], CHUNK_F * k, r * p.C + cb * CB, policy);
+#endif
   };
   // refill buffer b with the tile NST ahead of tile k of the current item (lane 0 only)
   auto refill = [&](long long cur, long long nxt, int k, int b) {
@@ -318,10 +334,9 @@ roi_align_bwd_cl(const __grid_constant__ CUtensorMap gmap, const Params p) {
   long long cur = fetch();
   long long nxt = cur < n_items ? fetch() : n_items;
   if (lane == 0 && cur < n_items) {
-    issue(cur, 0, 0);
-    issue(cur, 1, 1);
+    for (int k = 0; k < NST; ++k) issue(cur, k, k);
   }
-  uint32_t cc = 0;  // tiles consumed by this warp: buffer = cc & 1, mbarrier phase parity = (cc >> 1) & 1
+  uint32_t cc = 0;  // tiles consumed by this warp: buffer = cc % NST, mbarrier phase parity = (cc / NST) & 1
   while (cur < n_items) {
     const int r = (int)(cur / nblk);
     const int cb = (int)(cur - (long long)r * nblk);
@@ -369,8 +384,8 @@ roi_align_bwd_cl(const __grid_constant__ CUtensorMap gmap, const Params p) {
         if (iy == 0 && ph < P) {
           const int half = ph & 1;
           if (half == 0) {
-            b = cc & 1;
-            mbar_wait(&wa->bar[b], (cc >> 1) & 1u);
+            b = cc % NST;
+            mbar_wait(&wa->bar[b], (cc / NST) & 1u);
             ++cc;
           }
           const float* ta = wa->stage[b] + lane * CHUNK_F + half * P;
@@ -405,8 +420,8 @@ roi_align_bwd_cl(const __grid_constant__ CUtensorMap gmap, const Params p) {
       // degenerate / foreign RoIs (mode 0) only drain their tiles; mode 2 evaluates every tap directly
 #pragma unroll 1
       for (int k = 0; k < NCHUNK; ++k) {
-        const int b = cc & 1;
-        mbar_wait(&wa->bar[b], (cc >> 1) & 1u);
+        const int b = cc % NST;
+        mbar_wait(&wa->bar[b], (cc / NST) & 1u);
         ++cc;
         if (mode == 2) direct_chunk(p, wa, wa->stage[b], img, k, lane);
         __syncwarp();
