@@ -129,6 +129,28 @@ def test_roi_align_backward_channel_lane(ops, shape):
     assert_close_rms(got.cpu(), ref, 1e-5, "roi_align bwd (channel-lane)", magnitude=mag)
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 50, 84, 96), (1, 128, 20, 30, 40), (3, 8, 7, 9, 10), (2, 16, 64, 96, 50)])
+def test_roi_align_backward_sorted_edge_rois(ops, shape):
+    """Sorted RoIs through the autograd-facing entry point: RoIs hanging over every border, zero-size, outside, thin,
+    whole-image, and one unclipped giant RoI (sampling grid 27 > 6 -> the direct path of the channel-lane kernel;
+    C = 8 / 16 -> the column-owner kernel)."""
+    n, c, h, w, per = shape
+    g = seeded(400 + c + h)
+    rois = _rois(n, per, h * 16, w * 16, g)
+    rois[0, 1:] = torch.tensor([-40.0, -30.0, 100.0, 90.0])
+    rois[1, 1:] = torch.tensor([0.0, 0.0, w * 16.0, h * 16.0])                 # whole image
+    rois[2, 1:] = torch.tensor([w * 16.0 - 20, h * 16.0 - 20, w * 16.0 + 60, h * 16.0 + 50])
+    rois[3, 1:] = torch.tensor([33.0, 47.0, 33.0, 47.0])                       # zero-size
+    rois[4, 1:] = torch.tensor([-500.0, -500.0, -100.0, -100.0])               # entirely outside
+    rois[5, 1:] = torch.tensor([5.0, 5.0, 9.0, w * 4.0])                        # thin
+    rois[6, 1:] = torch.tensor([-2000.0, -1500.0, 4000.0, 3000.0])             # unclipped giant: fixup path
+    gout = torch.randn(rois.shape[0], c, 14, 14, generator=g)
+    ref = torch.ops.torchvision._roi_align_backward(gout, rois, 1.0 / 16, 14, 14, n, c, h, w, 0, True)
+    mag = torch.ops.torchvision._roi_align_backward(gout.abs(), rois, 1.0 / 16, 14, 14, n, c, h, w, 0, True)
+    got = ops.roi_align_backward(gout.cuda(), rois.cuda(), (n, c, h, w), 1.0 / 16, 0, True, True)
+    assert_close_rms(got.cpu(), ref, 1e-5, "roi_align bwd (sorted, edge RoIs)", magnitude=mag)
+
+
 def test_roi_align_linearity_full_size(ops):
     """Size-independent property at BASELINE.json's full size: ROIAlign is linear in the feature map, and
     <roi_align(f), g> == <f, roi_align_bwd(g)> (adjointness of forward and backward)."""
