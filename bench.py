@@ -456,6 +456,55 @@ def run_ours(args):
                            for k, v in kernel_ms.items()},
         }
 
+    # auxiliary: the inference side of the stage (decode / filter / NMS are launch-latency bound; reported
+    # per launch, not as a roofline claim).  configs[0]: VOC, 2 images x 512 proposals; configs[3]-sized decode + NMS.
+    aux = None
+    if rank == 0 and not args.no_aux:
+        from unit_b200 import layers
+        aux = {}
+        with torch.no_grad():
+            wl.head.eval()
+            g = _seeded(31)
+            f, pr, _, _ = make_inputs(3000)
+            props = [wl.Instances(IMG_HW, proposal_boxes=wl.Boxes(p[:512].to(device)),
+                                  objectness_logits=torch.zeros(512, device=device)) for p in pr]
+            feats = f.to(device)
+            xi, xwi = wl.x[:1024], wl.xw[:1024]
+            infer_stage = type(wl.stage)(wl.head, lambda pooled: (xi, xwi))
+            run = lambda: infer_stage.infer(feats, props)
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                run()
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) / 20 * 1e3
+            aux["voc_inference"] = {"images_per_s": N_IMG / (ms * 1e-3), "ms_per_call": ms,
+                                    "what": "RoIStage.infer, 2 images x 512 proposals, K=20: ROIAlign fwd -> transfer "
+                                            "-> softmax+decode -> filter -> class-wise NMS -> top-100 (wall clock, "
+                                            "includes the one D2H of the detection counts)"}
+            # COCO-sized decode + filter + NMS: 2 images x 1000 proposals x 80 classes
+            R, K = 2000, 80
+            scores = torch.softmax(4.0 * torch.randn(R, K + 1, generator=g), -1).to(device)
+            deltas = (0.2 * torch.randn(R, 4 * K, generator=g)).to(device)
+            pb = torch.cat([_boxes(1000, IMG_HW[0], IMG_HW[1], g) for _ in range(2)]).to(device)
+            off = ops.offsets_from_counts([1000, 1000], device)
+            hw = torch.tensor([[float(IMG_HW[0]), float(IMG_HW[1])]] * 2, device=device)
+
+            def dec_nms():
+                _, boxes = ops.softmax_decode(None, deltas, pb, want_probs=False)
+                return ops.detect(boxes, scores, off, hw, 0.05, 0.5, 100)
+
+            for _ in range(3):
+                out = dec_nms()
+            n_cand = int(out[5][4].sum().item())
+            aux["coco_decode_filter_nms"] = {
+                "ms_per_call": time_kernel(dec_nms, 10, flush), "candidates": n_cand,
+                "what": "softmax_decode + detect (filter, segmented NMS, top-100) for 2 images x 1000 proposals x 80 "
+                        "classes, CUDA events, L2 flushed; three launches"}
+            wl.head.train()
+
     # CPU baseline on the box's host cores (rank 0, N = 1 only): the oracle port on a bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -492,7 +541,7 @@ def run_ours(args):
             "gpu_launches_note": "kernels of libunit_b200.so executed in the timed region, directly or as nodes of "
                                  "the replayed CUDA graphs (cuBLAS GEMMs and ATen kernels not counted)",
             "cuda_graphs": bool(wl.use_graph),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "aux": aux,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -508,6 +557,7 @@ def main():
     ap.add_argument("--dtype", choices=["f32", "bf16"], default="f32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary inference-side measurements")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
