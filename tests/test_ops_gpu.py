@@ -391,6 +391,52 @@ def test_label_and_sample_bit_exact(ops):
     assert out_off == S
 
 
+def test_label_and_sample_full_batch_64_images(ops):
+    """BASELINE.json configs[2] size: 64 images x 1000 proposals (+GT) in ONE batched call of the public
+    ``layers.label_and_sample`` vs the per-image [D2] sequence of the oracle with the same generator stream."""
+    from oracle.d2.ops import MatcherWithVals, subsample_labels
+    from oracle.d2.structures import Boxes as RBoxes, pairwise_iou
+    from unit_b200 import layers
+    from unit_b200.structures import Boxes, Instances
+
+    g = seeded(640)
+    K, n_img = 20, 64
+    props, tgts, cpu = [], [], []
+    for i in range(n_img):
+        n_gt = int(torch.randint(0, 9, (1,), generator=g))
+        gt = random_boxes(n_gt, 800, 1333, g, 32.0)
+        pr = random_boxes(1000, 800, 1333, g, 16.0)
+        if n_gt:
+            k = 250
+            src = gt[torch.randint(0, n_gt, (k,), generator=g)]
+            wh = torch.cat([src[:, 2:] - src[:, :2]] * 2, 1)
+            pr[:k] = (src + 0.2 * (torch.rand(k, 4, generator=g) - 0.5) * wh).clamp(min=0)
+        gc = torch.randint(0, K, (n_gt,), generator=g)
+        allp = torch.cat([pr, gt])  # [D2] add_ground_truth_to_proposals: GT appended after the proposals
+        cpu.append((allp, gt, gc))
+        props.append(Instances((800, 1333), proposal_boxes=Boxes(allp.cuda()),
+                               objectness_logits=torch.zeros(len(allp), device="cuda")))
+        tgts.append(Instances((800, 1333), gt_boxes=Boxes(gt.cuda()), gt_classes=gc.cuda()))
+    out, _, _ = layers.label_and_sample(props, tgts, num_classes=K, batch_size_per_image=512, positive_fraction=0.25,
+                                        thresholds=[0.5], labels=[0, 1], generator=seeded(7))
+    gen = seeded(7)
+    ref = MatcherWithVals([0.5], [0, 1])
+    for i, (allp, gt, gc) in enumerate(cpu):
+        rm, rl, _ = ref(pairwise_iou(RBoxes(gt), RBoxes(allp)))
+        if len(gt):
+            cls = gc[rm]
+            cls[rl == 0] = K
+            cls[rl == -1] = -1
+        else:
+            cls = torch.zeros_like(rm) + K
+        p_idx, n_idx = subsample_labels(cls, 512, 0.25, K, generator=gen)
+        s_ref = torch.cat([p_idx, n_idx])
+        assert torch.equal(out[i].proposal_boxes.tensor.cpu(), allp[s_ref]), i
+        assert torch.equal(out[i].gt_classes.cpu(), cls[s_ref]), i
+        if len(gt):
+            assert torch.equal(out[i].gt_boxes.tensor.cpu(), gt[rm[s_ref]]), i
+
+
 # ----------------------------------------------------------------------------------------------- transfer
 def _spec_from_golden(ops, gold, lingual_soft, dev):
     terms = gold["terms"]

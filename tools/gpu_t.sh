@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest11.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/pytest11.log
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest12.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest12.log
