@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-for v in nored sametile both; do
-  echo "== $v"; UNIT_B200_LIB=$PWD/unit_b200/build/variants/lib_$v.so timeout 200 python tools/micro_roi.py 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ours_bwd_ms'], d['ours_fwd_ms'])"
-done
+for promo in 0 1 2 3; do for ef in 0 1; do
+  echo "== promo $promo evict_first $ef"; UNIT_ROI_BWD_PROMO=$promo UNIT_ROI_BWD_EVICT_FIRST=$ef timeout 200 python tools/micro_roi.py 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ours_bwd_ms'])"
+done; done

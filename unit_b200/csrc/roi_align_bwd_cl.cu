@@ -495,9 +495,15 @@ int launch_bwd_cl(const void* gout, const float* rois, void* gfeat, void* ws, in
     cuuint64_t strides[1] = {(cuuint64_t)(P * P) * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)CHUNK_F, (cuuint32_t)CB};
     cuuint32_t estr[2] = {1, 1};
+    const char* ep = getenv("UNIT_ROI_BWD_PROMO");
+    const int promo = ep ? atoi(ep) : 2;
+    const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                     : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                     : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                  : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     CUresult rc = encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(gout), dims, strides, box,
-                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, pr,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     UNIT_REQUIRE(rc == CUDA_SUCCESS, "roi_align_bwd: cuTensorMapEncodeTiled failed (%d)", (int)rc);
   }
   Params p;
