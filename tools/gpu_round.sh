@@ -1,10 +1,14 @@
+#!/bin/bash
+# One GPU-box pass of everything the round is judged on (run through gpurun; writes into gpurun_out/):
+#   parity tests, both bench arms, the ncu launch list of the bench, ncu --set full of the two ROIAlign kernels and the
+#   tcgen05 GEMM, compute-sanitizer over the op tests.  Summaries for profiles/ come from tools/ncu_summary.py.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest9.log 2>&1; echo "pytest rc=$?"
-timeout 200 python tools/gemm_diag.py > gpurun_out/gemm_diag2.log 2>&1
-timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench4.log 2>&1
-timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench4_ref.log 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_list2.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:roi_align_fwd_slab2 -c 1 -o gpurun_out/roi_fwd_v3 -f python tools/roi_only.py fwd > gpurun_out/ncu_fwd3.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:roi_align_bwd_slab2 -c 1 -o gpurun_out/roi_bwd_v4 -f python tools/roi_only.py bwd > gpurun_out/ncu_bwd4.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:tf32_gemm_kernel -c 1 -o gpurun_out/gemm_tf32 -f python tools/gemm_only.py > gpurun_out/ncu_gemm.log 2>&1
-tail -3 gpurun_out/pytest9.log; cat gpurun_out/gemm_diag2.log | tail -20; tail -2 gpurun_out/bench4.log; tail -1 gpurun_out/bench4_ref.log
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_final.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_final.log
+timeout 400 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_final.log 2>&1; tail -1 gpurun_out/bench_final.log | cut -c1-400
+timeout 400 python bench.py --impl reference --steps 2 --warmup 3 > gpurun_out/bench_final_ref.log 2>&1; tail -1 gpurun_out/bench_final_ref.log | cut -c1-200
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke_final.log 2>&1; tail -1 gpurun_out/smoke_final.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-aux > gpurun_out/ncu_list_final.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:roi_align_fwd_band -c 1 -o gpurun_out/roi_fwd_final -f python tools/roi_only.py fwd > gpurun_out/ncu_fwd_final.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:roi_align_bwd_cl -c 1 -o gpurun_out/roi_bwd_final -f python tools/roi_only.py bwd > gpurun_out/ncu_bwd_final.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:tf32_gemm_kernel -c 1 -o gpurun_out/gemm_final -f python tools/gemm_only.py > gpurun_out/ncu_gemm_final.log 2>&1
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_ops_gpu.py tests/test_gemm_gpu.py -m gpu -q -k "not full_size and not full_batch" > gpurun_out/sanitizer_final.log 2>&1; echo "memcheck rc=$?"; tail -2 gpurun_out/sanitizer_final.log
