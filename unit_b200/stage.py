@@ -25,6 +25,7 @@ class RoIStage:
         self.box_head_fn = box_head_fn
         self.bucket = bucket
         self._graphs: Dict[tuple, "_StepGraphs"] = {}
+        self.max_graphs = 8  # captured (input buffers, sample counts) keys kept alive; each holds its pooled tensors
         self.graph_launches = 0  # library kernels executed through graph replays (not visible to unit_launch_count)
 
     # ------------------------------------------------------------------------------------------- inference
@@ -127,6 +128,8 @@ class RoIStage:
                tuple(t.gt_classes.data_ptr() for t in targets))
         st = self._graphs.get(key)
         if st is None:
+            while len(self._graphs) >= self.max_graphs:  # callers that do not reuse buffers must not leak graphs
+                self._graphs.pop(next(iter(self._graphs)))
             st = _StepGraphs(self, features, proposals, targets, grad_pooled_fn)
             self._graphs[key] = st
         return st.run()
