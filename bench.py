@@ -471,16 +471,20 @@ def run_ours(args):
             feats = f.to(device)
             xi, xwi = wl.x[:1024], wl.xw[:1024]
             infer_stage = type(wl.stage)(wl.head, lambda pooled: (xi, xwi))
-            run = lambda: infer_stage.infer(feats, props)
-            for _ in range(3):
-                run()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(20):
-                run()
-            torch.cuda.synchronize()
-            ms = (time.perf_counter() - t0) / 20 * 1e3
+            def wall_ms(fn):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(20):
+                    fn()
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t0) / 20 * 1e3
+
+            ms_eager = wall_ms(lambda: infer_stage.infer(feats, props))
+            ms = ms_eager if not wl.use_graph else wall_ms(lambda: infer_stage.infer_graphed(feats, props))
             aux["voc_inference"] = {"images_per_s": N_IMG / (ms * 1e-3), "ms_per_call": ms,
+                                    "ms_per_call_eager": ms_eager, "cuda_graph": bool(wl.use_graph),
                                     "what": "RoIStage.infer, 2 images x 512 proposals, K=20: ROIAlign fwd -> transfer "
                                             "-> softmax+decode -> filter -> class-wise NMS -> top-100 (wall clock, "
                                             "includes the one D2H of the detection counts)"}

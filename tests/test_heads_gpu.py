@@ -307,6 +307,41 @@ def test_graphed_train_step_matches_eager(registry):
     assert st_g.graph_launches > 0 and len(st_g._graphs) == 1
 
 
+def test_graphed_inference_matches_eager(registry):
+    """RoIStage.infer_graphed (one CUDA graph up to the padded detections) == RoIStage.infer, call after call."""
+    from unit_b200.stage import RoIStage
+    from unit_b200.structures import Boxes, Instances
+
+    cfg, head = _build("voc_split1_ft.yaml", 64, registry)
+    g = seeded(55)
+    with torch.no_grad():
+        for name, p in sorted(head.named_parameters()):
+            if "embeddings" not in name:
+                p.copy_(torch.randn(p.shape, generator=g) * (0.02 if "bbox" in name else 0.2))
+    head = head.cuda().eval()
+
+    def box_head_fn(pooled):
+        m = pooled.mean(dim=[2, 3])
+        return torch.relu(head.box_head.proj(m)), torch.relu(head.weak_box_head.proj(m))
+
+    stage = RoIStage(head, box_head_fn)
+    img = (400, 672)
+    feats = torch.randn(2, 64, 25, 42, generator=g).cuda()
+    props = [Instances(img, proposal_boxes=Boxes(random_boxes(300, img[0], img[1], g, 16.0).cuda()),
+                       objectness_logits=torch.zeros(300, device="cuda")) for _ in range(2)]
+    for it in range(3):
+        if it == 2:  # new contents in the SAME buffers: the replayed graph must see them
+            feats.copy_(torch.randn(2, 64, 25, 42, generator=g))
+        ref, ref_kept = stage.infer(feats, props)
+        got, got_kept = stage.infer_graphed(feats, props)
+        for a, b, ka, kb in zip(ref, got, ref_kept, got_kept):
+            assert torch.equal(ka, kb)
+            assert torch.equal(a.pred_classes, b.pred_classes)
+            assert torch.equal(a.scores, b.scores)
+            assert torch.equal(a.pred_boxes.tensor, b.pred_boxes.tensor)
+    assert sum(1 for k in stage._graphs if k[0] == "infer") == 1
+
+
 def test_mask_head_inference_coco(registry):
     from unit_b200.structures import Boxes, Instances
 

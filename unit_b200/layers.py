@@ -318,21 +318,23 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, i
 
 
 # ------------------------------------------------------------------------------------------------- inference
-def fast_rcnn_inference(boxes: Sequence[torch.Tensor], scores: Sequence[torch.Tensor],
-                        image_shapes: Sequence[Tuple[int, int]], score_thresh: float, nms_thresh: float,
-                        topk_per_image: int, nms_mode: int = ops.NMS_TV_CUDA_RULE):
-    """[D2] ``fast_rcnn_inference`` (fast_rcnn.py:461-468, weak_detector_fast_rcnn.py:299-306, rcnn.py:526):
-    all images in two launches and one host read of the detection counts.
-    Returns (List[Instances(pred_boxes, scores, pred_classes)], List[kept RoI index])."""
-    n_img = len(boxes)
-    if n_img == 0:
-        return [], []
+def fast_rcnn_inference_device(boxes: Sequence[torch.Tensor], scores: Sequence[torch.Tensor],
+                                image_shapes: Sequence[Tuple[int, int]], score_thresh: float, nms_thresh: float,
+                                topk_per_image: int, nms_mode: int = ops.NMS_TV_CUDA_RULE):
+    """Device half of ``fast_rcnn_inference``: filter + class-wise NMS + top-k for all images in two launches, nothing
+    read back (capturable).  Returns padded (det_boxes [n,topk,4], det_scores, det_classes, det_roi, det_counts)."""
     dev = boxes[0].device
     counts = [b.shape[0] for b in boxes]
     off = ops.offsets_from_counts(counts, dev)
-    hw = torch.tensor([[float(h), float(w)] for (h, w) in image_shapes], dtype=torch.float32, device=dev)
+    hw = ops.f32_const([[float(h), float(w)] for (h, w) in image_shapes], dev)
     db, ds, dc, dr, cnt, _ = ops.detect(cat(list(boxes)), cat(list(scores)), off, hw, score_thresh, nms_thresh,
                                         topk_per_image, nms_mode)
+    return db, ds, dc, dr, cnt
+
+
+def instances_from_detections(dets, image_shapes: Sequence[Tuple[int, int]]):
+    """Host half: ONE read of the per-image detection counts, then views of the padded device outputs."""
+    db, ds, dc, dr, cnt = dets
     cnt_h = cnt.cpu().tolist()
     results, kept = [], []
     for i, shape in enumerate(image_shapes):
@@ -344,6 +346,18 @@ def fast_rcnn_inference(boxes: Sequence[torch.Tensor], scores: Sequence[torch.Te
         results.append(inst)
         kept.append(dr[i, :n])
     return results, kept
+
+
+def fast_rcnn_inference(boxes: Sequence[torch.Tensor], scores: Sequence[torch.Tensor],
+                        image_shapes: Sequence[Tuple[int, int]], score_thresh: float, nms_thresh: float,
+                        topk_per_image: int, nms_mode: int = ops.NMS_TV_CUDA_RULE):
+    """[D2] ``fast_rcnn_inference`` (fast_rcnn.py:461-468, weak_detector_fast_rcnn.py:299-306, rcnn.py:526):
+    all images in two launches and one host read of the detection counts.
+    Returns (List[Instances(pred_boxes, scores, pred_classes)], List[kept RoI index])."""
+    if len(boxes) == 0:
+        return [], []
+    dets = fast_rcnn_inference_device(boxes, scores, image_shapes, score_thresh, nms_thresh, topk_per_image, nms_mode)
+    return instances_from_detections(dets, image_shapes)
 
 
 def mask_rcnn_inference(pred_mask_logits: torch.Tensor, pred_instances: List[Instances]) -> None:

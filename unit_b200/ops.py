@@ -74,6 +74,21 @@ def _i32(values: Sequence[int], dev: torch.device) -> torch.Tensor:
     return t
 
 
+_F32_CACHE = {}
+
+
+def f32_const(values: Sequence[Sequence[float]], dev: torch.device) -> torch.Tensor:
+    """Small read-only fp32 device array (image sizes ...), cached by value like ``_i32``."""
+    key = (tuple(tuple(float(x) for x in row) for row in values), str(dev))
+    t = _F32_CACHE.get(key)
+    if t is None:
+        if len(_F32_CACHE) >= 512:
+            _F32_CACHE.clear()
+        t = torch.tensor([list(r) for r in key[0]], dtype=torch.float32, device=dev)
+        _F32_CACHE[key] = t
+    return t
+
+
 def offsets_from_counts(counts: Sequence[int], dev: torch.device) -> torch.Tensor:
     off = [0]
     for c in counts:

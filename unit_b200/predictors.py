@@ -384,11 +384,20 @@ class SupervisedDetectorOutputsBase(nn.Module):
         if tta:
             probs, _ = ops.softmax_decode(scores, None, None, want_boxes=False)
             return [probs, predictions[1]], None
+        dets = self.inference_device(predictions, proposals)
+        return layers.instances_from_detections(dets, [x.image_size for x in proposals])
+
+    def inference_device(self, predictions, proposals):
+        """Device half of ``inference`` (softmax + decode, filter, NMS, top-k): nothing is read back, so it can be
+        captured in a CUDA graph; ``layers.instances_from_detections`` finishes on the host."""
+        scores, proposal_deltas = predictions
+        n = [len(p) for p in proposals]
         boxes_in = layers.cat([p.proposal_boxes.tensor for p in proposals])
         probs, boxes = ops.softmax_decode(scores, proposal_deltas, boxes_in, self.box2box_transform.weights,
                                           self.box2box_transform.scale_clamp)
-        return fast_rcnn_inference(boxes.split(n), probs.split(n), [x.image_size for x in proposals],
-                                   self.test_score_thresh, self.test_nms_thresh, self.test_topk_per_image)
+        return layers.fast_rcnn_inference_device(boxes.split(n), probs.split(n), [x.image_size for x in proposals],
+                                                 self.test_score_thresh, self.test_nms_thresh,
+                                                 self.test_topk_per_image)
 
 
     def inference_tta(self, tta_predictions, proposals):

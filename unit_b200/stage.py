@@ -42,6 +42,43 @@ class RoIStage:
         return head.box_predictor.inference(predictions, proposals)
 
     @torch.no_grad()
+    def infer_graphed(self, features: torch.Tensor, proposals: List[Instances]):
+        """``infer`` with everything up to the padded detections replayed from one CUDA graph (keyed by the input
+        buffers, which the caller must reuse); the only host work per call is the read of the detection counts.  The
+        returned Instances are views of the graph's static outputs: consume them before the next call with that key."""
+        head = self.head
+        head.move_mappings_to_gpu()
+        key = ("infer", features.data_ptr(), tuple(features.shape),
+               tuple(p.proposal_boxes.tensor.data_ptr() for p in proposals), tuple(len(p) for p in proposals))
+        st = self._graphs.get(key)
+        if st is None:
+            while len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
+
+            def device_part():
+                pooled = head.box_pooler([features], [p.proposal_boxes for p in proposals])
+                x, xw = self.box_head_fn(pooled)
+                sim = head.get_similarity_matrices(x)
+                predictions, _ = head.box_predictor(x, supervised_branch_x_weak=xw,
+                                                    novel_classes=head._novel_classes_tensor,
+                                                    base_classes=head._base_classes_tensor, similarity=sim)
+                return head.box_predictor.inference_device(predictions, proposals)
+
+            dev = features.device
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):  # warm-up outside capture: lazy handles, workspaces, cached constants
+                device_part()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                dets = device_part()
+            st = (graph, dets)
+            self._graphs[key] = st
+        st[0].replay()
+        return layers.instances_from_detections(st[1], [p.image_size for p in proposals])
+
+    @torch.no_grad()
     def infer_tta(self, features: Sequence[torch.Tensor], aug_proposals: Sequence[List[Instances]],
                   proposals: List[Instances]):
         """rcnn.py:495-527: one pass per augmentation (its own feature map and transformed proposals, same RoI order)
