@@ -1,0 +1,1 @@
+"""Stand-in for the parts of Detectron2 the reference path imports (test infrastructure only; see oracle/__init__.py)."""
