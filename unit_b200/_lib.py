@@ -76,6 +76,13 @@ def lib() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH) and "UNIT_B200_LIB" not in os.environ:
+        # the library normally travels with the tree; a bare source checkout on a box with nvcc builds it once
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception:  # no nvcc / compile error: fall through to the explicit failure below
+            pass
     if not os.path.exists(LIB_PATH):
         raise UnitLibraryError(
             f"{LIB_PATH} is missing: build it with `python -m unit_b200.build` (needs nvcc). "
