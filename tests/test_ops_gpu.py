@@ -292,8 +292,12 @@ def test_plain_nms_and_ties(ops):
     assert ops.nms(boxes[:0].cuda(), scores[:0].cuda(), 0.5).numel() == 0
 
 
-@pytest.mark.parametrize("K,R", [(20, 512), (80, 1000)])
-def test_fast_rcnn_inference_batched_bit_exact(ops, K, R):
+@pytest.mark.parametrize("K,R,thresh", [(20, 512, 0.05), (80, 1000, 0.05), (80, 1000, 0.003), (3, 700, 0.01),
+                                          (2, 6000, 0.01)])
+def test_fast_rcnn_inference_batched_bit_exact(ops, K, R, thresh):
+    """Filter + class-wise NMS + top-k vs [D2] fast_rcnn_inference.  The grouped multi-CTA NMS takes the first two
+    cases; thresh 0.003 leaves > 16384 candidates per image (segmented single-CTA kernel); K = 2 with 6000 proposals puts > 4096 candidates of one image in
+    one class group (also the segmented kernel); K = 3 leaves most groups empty."""
     from oracle.d2.ops import fast_rcnn_inference
 
     g = seeded(70 + K)
@@ -309,13 +313,13 @@ def test_fast_rcnn_inference_batched_bit_exact(ops, K, R):
         probs.append(p)
     boxes[1][5, 3] = float("nan")       # non-finite rows are dropped and the returned roi index shifts
     probs[1][9, 2] = float("inf")
-    ref_inst, ref_idx = fast_rcnn_inference(boxes, probs, sizes, 0.05, 0.5, 100)
+    ref_inst, ref_idx = fast_rcnn_inference(boxes, probs, sizes, thresh, 0.5, 100)
     dev = torch.device("cuda")
     off = ops.offsets_from_counts([R] * n_img, dev)
     hw = torch.tensor(sizes, dtype=torch.float32, device=dev)
     for mode in (ops.NMS_TV_CPU_RULE,):
-        db, ds, dc, dr, cnt, _ = ops.detect(torch.cat(boxes).cuda(), torch.cat(probs).cuda(), off, hw, 0.05, 0.5, 100,
-                                            nms_mode=mode)
+        db, ds, dc, dr, cnt, _ = ops.detect(torch.cat(boxes).cuda(), torch.cat(probs).cuda(), off, hw, thresh, 0.5,
+                                            100, nms_mode=mode)
         cnt = cnt.cpu().tolist()
         for i in range(n_img):
             n = cnt[i]

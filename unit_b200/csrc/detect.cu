@@ -228,6 +228,7 @@ struct NmsParams {
   int64_t* det_roi;
   const int* cand_roi;
   int det_stride;
+  const unsigned char* seg_enable;  // optional: segments whose byte is 0 are skipped (handled by the grouped path)
   unsigned long long* ws_key1;  // global fallback arrays, indexed from 2 * segment offset
   unsigned long long* ws_key2;
   float4* ws_box;
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(NT, 1) segmented_nms_kernel(const NmsParams p)
   __shared__ float s_red[64];
 
   const int seg = blockIdx.x;
+  if (p.seg_enable && !p.seg_enable[seg]) return;
   const int n = p.seg_counts ? p.seg_counts[seg] : p.n_single;
   const long long base = p.seg_base ? (long long)p.seg_base[seg] * p.seg_mul : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -503,6 +505,250 @@ __global__ void __launch_bounds__(NT, 1) segmented_nms_kernel(const NmsParams p)
   if (tid == 0 && p.keep_counts) p.keep_counts[seg] = min(kept_before, limit);
 }
 
+// ---------------------------------------------------------------------------------------- grouped NMS (detections)
+// fast_rcnn_inference runs NMS class by class, so one image does not have to be one CTA: NG CTAs per image each take
+// the classes c with c % NG == g, sort only their candidates by (class, score desc, index asc), run the same greedy
+// reduction (same fp32 IoU arithmetic, same coordinate-trick shift, so the keep set is bit-identical) and mark the
+// survivors; a second kernel per image sorts the survivors by (score desc, index asc) and writes the top-k.  Images
+// that do not fit the grouped path (all-pairs fallback of the coordinate trick, a group over GCAP, > TOPCAP
+// candidates) are flagged and handled by segmented_nms_kernel.
+constexpr int NG = 8;
+constexpr int GT = 512;
+constexpr int GCAP = 4096;
+constexpr int TOPCAP = 16384;
+
+struct GroupParams {
+  const float4* boxes;
+  const float* scores;
+  const int* cls;
+  const int* counts;
+  const int* seg_base;
+  int seg_mul;
+  float thr;
+  int mode;
+  unsigned char* keep_flag;  // [total candidates]
+  unsigned char* use_old;    // [n_img]
+  // top-k outputs
+  int max_keep, det_stride;
+  float4* det_boxes;
+  float* det_scores;
+  int64_t* det_classes;
+  int64_t* det_roi;
+  const int* cand_roi;
+  int* det_counts;
+};
+
+template <int THREADS>
+__device__ void bitonic_sort_t(unsigned long long* key, int n_pad) {
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pad; i += THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = key[i], b = key[ixj];
+          const bool asc = (i & k) == 0;
+          if ((a > b) == asc) {
+            key[i] = b;
+            key[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GT) nms_group_kernel(const GroupParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  float4* sbox = reinterpret_cast<float4*>(keys + GCAP);
+  int* flag = reinterpret_cast<int*>(sbox + GCAP);
+  __shared__ int s_cnt[NG];
+  __shared__ int s_m;
+  __shared__ float s_red[2 * (GT / 32)];
+  const int g = blockIdx.x, img = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = p.counts[img];
+  if (n <= 0) return;
+  const long long base = (long long)p.seg_base[img] * p.seg_mul;
+  const float4* boxes = p.boxes + base;
+  const float* scores = p.scores + base;
+  const int* cls = p.cls + base;
+  if (tid < NG) s_cnt[tid] = 0;
+  if (tid == 0) s_m = 0;
+  __syncthreads();
+
+  // group sizes (every CTA of the image computes all of them: one consistent decision) and the coordinate range
+  float mx = -INFINITY, mn = INFINITY;
+  for (int i = tid; i < n; i += GT) {
+    atomicAdd(&s_cnt[cls[i] % NG], 1);
+    const float4 b = boxes[i];
+    mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+    mn = fminf(mn, fminf(fminf(b.x, b.y), fminf(b.z, b.w)));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if (lane == 0) {
+    s_red[warp] = mx;
+    s_red[GT / 32 + warp] = mn;
+  }
+  __syncthreads();
+  mx = s_red[0];
+  mn = s_red[GT / 32];
+  for (int w = 1; w < GT / 32; ++w) {
+    mx = fmaxf(mx, s_red[w]);
+    mn = fminf(mn, s_red[GT / 32 + w]);
+  }
+  int mode = p.mode;  // torchvision ops/boxes.py:80
+  if (mode == 2) mode = (4LL * n > 100000) ? 0 : 1;
+  if (mode == 3) mode = (4LL * n > 4000) ? 0 : 1;
+  const float off_unit = __fadd_rn(mx, 1.f);
+  bool old = n > TOPCAP;
+  if (mode == 1 && (!(mn >= -1.f) || !(p.thr >= 0.f))) old = true;  // literal all-pairs formulation
+  for (int q = 0; q < NG; ++q) old |= s_cnt[q] > GCAP;
+  if (tid == 0) p.use_old[img] = old ? 1 : 0;
+  if (old) return;
+  const int m = s_cnt[g];
+  if (m == 0) return;
+  int m_pad = 1;
+  while (m_pad < m) m_pad <<= 1;
+
+  // this group's candidates: key = class | score descending | index ascending
+  for (int i = tid; i < n; i += GT) {
+    const int c = cls[i];
+    if (c % NG == g) {
+      const int pos = atomicAdd(&s_m, 1);
+      keys[pos] = ((unsigned long long)(unsigned)c << 49) | ((unsigned long long)(~ordered_u32(scores[i])) << 17) |
+                  (unsigned long long)i;
+    }
+  }
+  for (int i = m + tid; i < m_pad; i += GT) keys[i] = ~0ull;
+  __syncthreads();
+  bitonic_sort_t<GT>(keys, m_pad);
+  for (int j = tid; j < m; j += GT) {
+    const unsigned idx = (unsigned)(keys[j] & 0x1ffffu);
+    float4 b = boxes[idx];
+    if (mode == 1) {
+      const float o = __fmul_rn((float)cls[idx], off_unit);
+      b.x = __fadd_rn(b.x, o);
+      b.y = __fadd_rn(b.y, o);
+      b.z = __fadd_rn(b.z, o);
+      b.w = __fadd_rn(b.w, o);
+    }
+    sbox[j] = b;
+    flag[j] = 0;
+  }
+  __syncthreads();
+
+  // greedy NMS per class segment (same reduction as segmented_nms_kernel)
+  {
+    int seg_ord = 0;
+    for (int j0 = 0; j0 < m; j0 += 32) {
+      const int j = j0 + lane;
+      bool start = false;
+      if (j < m) start = (j == 0) || ((keys[j] >> 49) != (keys[j - 1] >> 49));
+      unsigned sm = __ballot_sync(0xffffffffu, start);
+      while (sm) {
+        const int l = __ffs(sm) - 1;
+        sm &= sm - 1;
+        const int s = j0 + l;
+        if ((seg_ord % (GT / 32)) == warp) {
+          const unsigned long long c = keys[s] >> 49;
+          int e;
+          {
+            int lo = s, hi = m;
+            while (hi - lo > 1) {
+              const int mid = (lo + hi) >> 1;
+              if ((keys[mid] >> 49) == c) lo = mid; else hi = mid;
+            }
+            e = lo + 1;
+          }
+          for (int c0 = s; c0 < e; c0 += 32) {
+            const int q = c0 + lane;
+            const bool valid = q < e;
+            float4 my = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) my = sbox[q];
+            const float my_area = box_area_rn(my.x, my.y, my.z, my.w);
+            bool alive = valid;
+            for (int t0 = s; t0 < c0; t0 += 32) {
+              unsigned km = (unsigned)flag[t0 + lane];
+              km = __ballot_sync(0xffffffffu, km != 0);
+              while (km) {
+                const int kl = __ffs(km) - 1;
+                km &= km - 1;
+                const float4 kb = sbox[t0 + kl];
+                const float inter = box_inter_rn(kb.x, kb.y, kb.z, kb.w, my.x, my.y, my.z, my.w);
+                const float iou = iou_from_rn(inter, box_area_rn(kb.x, kb.y, kb.z, kb.w), my_area);
+                if (iou > p.thr) alive = false;
+              }
+              if (!__any_sync(0xffffffffu, alive)) break;
+            }
+            for (int l2 = 0; l2 < 32; ++l2) {
+              const unsigned am = __ballot_sync(0xffffffffu, alive);
+              if (!((am >> l2) & 1u)) continue;
+              if ((am >> l2) <= 1u) break;
+              const float kx = __shfl_sync(0xffffffffu, my.x, l2), ky = __shfl_sync(0xffffffffu, my.y, l2);
+              const float kz = __shfl_sync(0xffffffffu, my.z, l2), kw = __shfl_sync(0xffffffffu, my.w, l2);
+              const float ka = __shfl_sync(0xffffffffu, my_area, l2);
+              if (alive && lane > l2) {
+                const float inter = box_inter_rn(kx, ky, kz, kw, my.x, my.y, my.z, my.w);
+                if (iou_from_rn(inter, ka, my_area) > p.thr) alive = false;
+              }
+            }
+            if (valid) flag[q] = alive ? 1 : 0;
+            __syncwarp();
+          }
+        }
+        ++seg_ord;
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < m; j += GT) p.keep_flag[base + (keys[j] & 0x1ffffu)] = (unsigned char)flag[j];
+}
+
+__global__ void __launch_bounds__(NT) nms_topk_kernel(const GroupParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  __shared__ int s_k;
+  const int img = blockIdx.x, tid = threadIdx.x;
+  const int n = p.counts[img];
+  if (n <= 0) {
+    if (tid == 0) p.det_counts[img] = 0;
+    return;
+  }
+  if (p.use_old[img]) return;
+  const long long base = (long long)p.seg_base[img] * p.seg_mul;
+  if (tid == 0) s_k = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += NT) {
+    if (p.keep_flag[base + i]) {
+      const int pos = atomicAdd(&s_k, 1);
+      keys[pos] = ((unsigned long long)(~ordered_u32(p.scores[base + i])) << 32) | (unsigned)i;
+    }
+  }
+  __syncthreads();
+  const int kk = s_k;
+  int k_pad = 1;
+  while (k_pad < kk) k_pad <<= 1;
+  for (int i = kk + tid; i < k_pad; i += NT) keys[i] = ~0ull;
+  __syncthreads();
+  bitonic_sort_t<NT>(keys, k_pad);
+  const int limit = p.max_keep >= 0 ? p.max_keep : n;
+  const int cnt = min(kk, limit);
+  for (int j = tid; j < cnt; j += NT) {
+    const unsigned idx = (unsigned)(keys[j] & 0xffffffffu);
+    const long long o = (long long)img * p.det_stride + j;
+    p.det_boxes[o] = p.boxes[base + idx];
+    p.det_scores[o] = p.scores[base + idx];
+    p.det_classes[o] = p.cls[base + idx];
+    p.det_roi[o] = p.cand_roi[base + idx];
+  }
+  if (tid == 0) p.det_counts[img] = cnt;
+}
+
 static size_t nms_smem_bytes() { return (size_t)SMEM_CAP * (8 + 8 + 16 + 4); }
 
 static int launch_nms(NmsParams& p, int n_seg, long long total, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -579,7 +825,8 @@ int unit_detect_filter(const float* boxes, const float* probs, const int* roi_of
 size_t unit_nms_workspace_bytes(int n_seg, int total_candidates) {
   (void)n_seg;
   const size_t M = 2 * (size_t)(total_candidates > 0 ? total_candidates : 0) + 64;
-  return 36 * M + 256;
+  // segmented kernel arrays + the grouped path's keep flags (1 B / candidate) and per-image switch
+  return 36 * M + 256 + (size_t)(total_candidates > 0 ? total_candidates : 0) + (size_t)(n_seg > 0 ? n_seg : 0) + 512;
 }
 
 int unit_detect_nms(const float* cand_boxes, const float* cand_scores, const int* cand_roi, const int* cand_cls,
@@ -610,7 +857,48 @@ int unit_detect_nms(const float* cand_boxes, const float* cand_scores, const int
   p.det_roi = det_roi;
   p.cand_roi = cand_roi;
   p.det_stride = topk;
-  return launch_nms(p, n_img, (long long)R * K, workspace, workspace_bytes, (cudaStream_t)stream);
+  const long long total = (long long)R * K;
+  if (K >= 2 && cand_cls && total < (1ll << 17) * 64 && !getenv("UNIT_NMS_SINGLE")) {
+    // grouped path: NG CTAs per image + a top-k kernel; images it cannot take fall through to the segmented kernel
+    const size_t need = unit_nms_workspace_bytes(n_img, (int)total);
+    if (!workspace || workspace_bytes < need) {
+      set_error("nms: workspace too small (%zu < %zu)", workspace_bytes, need);
+      return UNIT_EWORKSPACE;
+    }
+    const size_t M = 2 * (size_t)total + 64;
+    unsigned char* flags = (unsigned char*)workspace + 36 * M + 256;
+    GroupParams gp = {};
+    gp.boxes = (const float4*)cand_boxes;
+    gp.scores = cand_scores;
+    gp.cls = cand_cls;
+    gp.counts = cand_counts;
+    gp.seg_base = roi_offsets;
+    gp.seg_mul = K;
+    gp.thr = nms_thresh;
+    gp.mode = nms_mode;
+    gp.keep_flag = flags;
+    gp.use_old = flags + total + 128;
+    gp.max_keep = topk;
+    gp.det_stride = topk;
+    gp.det_boxes = (float4*)det_boxes;
+    gp.det_scores = det_scores;
+    gp.det_classes = det_classes;
+    gp.det_roi = det_roi;
+    gp.cand_roi = cand_roi;
+    gp.det_counts = det_counts;
+    cudaStream_t st = (cudaStream_t)stream;
+    UNIT_CUDA(cudaMemsetAsync(gp.use_old, 1, (size_t)n_img, st));  // images with no candidates stay "old": harmless
+    const size_t gsm = (size_t)GCAP * (8 + 16 + 4);
+    UNIT_CUDA(cudaFuncSetAttribute(nms_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+    nms_group_kernel<<<dim3(NG, n_img), GT, gsm, st>>>(gp);
+    UNIT_CHECK_LAUNCH("nms_group_kernel");
+    const size_t tsm = (size_t)TOPCAP * 8;
+    UNIT_CUDA(cudaFuncSetAttribute(nms_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+    nms_topk_kernel<<<n_img, NT, tsm, st>>>(gp);
+    UNIT_CHECK_LAUNCH("nms_topk_kernel");
+    p.seg_enable = gp.use_old;
+  }
+  return launch_nms(p, n_img, total, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int unit_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int N, float iou_thresh,
