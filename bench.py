@@ -505,8 +505,8 @@ def run_ours(args):
             n_cand = int(out[5][4].sum().item())
             aux["coco_decode_filter_nms"] = {
                 "ms_per_call": time_kernel(dec_nms, 10, flush), "candidates": n_cand,
-                "what": "softmax_decode + detect (filter, segmented NMS, top-100) for 2 images x 1000 proposals x 80 "
-                        "classes, CUDA events, L2 flushed; three launches"}
+                "what": "softmax_decode + detect (parallel filter, grouped NMS, top-100) for 2 images x 1000 proposals "
+                        "x 80 classes, CUDA events, L2 flushed"}
             wl.head.train()
 
     # CPU baseline on the box's host cores (rank 0, N = 1 only): the oracle port on a bounded sample

@@ -131,6 +131,7 @@ int unit_fastrcnn_loss(const float* scores, const float* deltas, const float* pr
  *   boxes [R,4*KB], probs [R,K+1], roi_offsets int32 [n_img+1], image_hw fp32 [n_img,2] (h,w), all device.
  * unit_detect_filter writes per-image candidate segments starting at roi_offsets[i]*K:
  *   cand_boxes [R*K,4], cand_scores [R*K], cand_roi/cand_cls int32 [R*K], cand_counts int32 [n_img].
+ *   workspace (optional, >= 8*R + 256 bytes; the NMS workspace can be passed): lets the filter spread over the GPU.
  * unit_detect_nms consumes them and writes det_* [n_img, topk(...)] + det_counts [n_img].
  *   nms_mode: 0 = class-wise on the raw boxes (torchvision _batched_nms_vanilla), 1 = coordinate trick
  *   (boxes + cls*(max+1), torchvision _batched_nms_coordinate_trick), 2 = follow torchvision's CUDA rule
@@ -138,7 +139,8 @@ int unit_fastrcnn_loss(const float* scores, const float* deltas, const float* pr
  */
 int unit_detect_filter(const float* boxes, const float* probs, const int* roi_offsets, const float* image_hw,
                        int n_img, int R, int K, int KB, float score_thresh, float* cand_boxes, float* cand_scores,
-                       int* cand_roi, int* cand_cls, int* cand_counts, unit_stream_t stream);
+                       int* cand_roi, int* cand_cls, int* cand_counts, void* workspace, size_t workspace_bytes,
+                       unit_stream_t stream);
 size_t unit_nms_workspace_bytes(int n_seg, int total_candidates);
 int unit_detect_nms(const float* cand_boxes, const float* cand_scores, const int* cand_roi, const int* cand_cls,
                     const int* cand_counts, const int* roi_offsets, int n_img, int R, int K, float nms_thresh,

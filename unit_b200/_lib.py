@@ -45,7 +45,7 @@ _SIGNATURES = {
     "unit_box_get_deltas": (c_int, [P, P, P, c_int, c_float, c_float, c_float, c_float, P]),
     "unit_fastrcnn_loss": (c_int, [P, P, P, P, P, c_int, c_int, c_float, c_float, c_float, c_float, c_float, P, P, P, P,
                                    c_size_t, P]),
-    "unit_detect_filter": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P]),
+    "unit_detect_filter": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P, c_size_t, P]),
     "unit_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
     "unit_detect_nms": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, P, P, P, P, P, P,
                                 c_size_t, P]),

@@ -203,6 +203,133 @@ __global__ void __launch_bounds__(FT) detect_filter_kernel(const float* __restri
   if (tid == 0) cand_counts[img] = base_cnt;
 }
 
+// ---------------------------------------------------------------------------------------- parallel candidate filter
+// Same result as detect_filter_kernel (candidates in row-major (roi, class) order, roi = rank among the image's finite
+// rows), but spread over the GPU: (1) one warp per row -> validity and candidate count, (2) one CTA per image -> exclusive
+// scans over its rows, (3) one warp per row -> emit at the scanned position.  Row arrays live in the caller's workspace.
+constexpr int FW = 8;  // warps (rows) per CTA
+
+__global__ void __launch_bounds__(FW * 32)
+filter_count_kernel(const float* __restrict__ boxes, const float* __restrict__ probs, int R, int K, int KB, float thresh,
+                    int* __restrict__ row_valid, int* __restrict__ row_cnt) {
+  const int r = blockIdx.x * FW + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int K1 = K + 1;
+  const float* b = boxes + (long long)r * KB * 4;
+  const float* s = probs + (long long)r * K1;
+  bool ok = true;
+  for (int i = lane; i < KB * 4; i += 32) ok &= finite_f(b[i]);
+  for (int i = lane; i < K1; i += 32) ok &= finite_f(s[i]);
+  ok = __all_sync(0xffffffffu, ok);
+  int cnt = 0;
+  if (ok)
+    for (int k0 = 0; k0 < K; k0 += 32) {
+      const int k = k0 + lane;
+      cnt += __popc(__ballot_sync(0xffffffffu, k < K && s[k] > thresh));
+    }
+  if (lane == 0) {
+    row_valid[r] = ok ? 1 : 0;
+    row_cnt[r] = cnt;
+  }
+}
+
+// per image: row_valid -> rank among valid rows (or -1), row_cnt -> first candidate slot; cand_counts[img] = total
+__global__ void __launch_bounds__(1024)
+filter_scan_kernel(const int* __restrict__ roi_off, int* __restrict__ row_valid, int* __restrict__ row_cnt,
+                   int* __restrict__ cand_counts) {
+  __shared__ int s_wv[32], s_wc[32], base_v, base_c, round_v, round_c;
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = roi_off[img], r1 = roi_off[img + 1];
+  if (tid == 0) {
+    base_v = 0;
+    base_c = 0;
+  }
+  __syncthreads();
+  for (int chunk = r0; chunk < r1; chunk += 1024) {
+    const int r = chunk + tid;
+    const int v = r < r1 ? row_valid[r] : 0, c = r < r1 ? row_cnt[r] : 0;
+    int sv = v, sc = c;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int tv = __shfl_up_sync(0xffffffffu, sv, o), tc = __shfl_up_sync(0xffffffffu, sc, o);
+      if (lane >= o) {
+        sv += tv;
+        sc += tc;
+      }
+    }
+    if (lane == 31) {
+      s_wv[warp] = sv;
+      s_wc[warp] = sc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int wv = s_wv[lane], wc = s_wc[lane];
+      int av = wv, ac = wc;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int tv = __shfl_up_sync(0xffffffffu, av, o), tc = __shfl_up_sync(0xffffffffu, ac, o);
+        if (lane >= o) {
+          av += tv;
+          ac += tc;
+        }
+      }
+      s_wv[lane] = av - wv;
+      s_wc[lane] = ac - wc;
+      if (lane == 31) {
+        round_v = av;
+        round_c = ac;
+      }
+    }
+    __syncthreads();
+    if (r < r1) {
+      row_valid[r] = v ? base_v + s_wv[warp] + sv - v : -1;
+      row_cnt[r] = base_c + s_wc[warp] + sc - c;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      base_v += round_v;
+      base_c += round_c;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) cand_counts[img] = base_c;
+}
+
+__global__ void __launch_bounds__(FW * 32)
+filter_emit_kernel(const float* __restrict__ boxes, const float* __restrict__ probs, const int* __restrict__ roi_off,
+                   const float* __restrict__ image_hw, int n_img, int R, int K, int KB, float thresh,
+                   const int* __restrict__ row_rank, const int* __restrict__ row_pos, float4* __restrict__ cand_boxes,
+                   float* __restrict__ cand_scores, int* __restrict__ cand_roi, int* __restrict__ cand_cls) {
+  const int r = blockIdx.x * FW + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int rank = row_rank[r];
+  if (rank < 0) return;
+  int img = 0;  // the image of row r (n_img is small: a linear walk of the offsets)
+  while (img + 1 < n_img && roi_off[img + 1] <= r) ++img;
+  const float img_h = image_hw[2 * img], img_w = image_hw[2 * img + 1];
+  const long long out0 = (long long)roi_off[img] * K;
+  const float* s = probs + (long long)r * (K + 1);
+  int pos = row_pos[r];
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int k = k0 + lane;
+    const float sc_k = k < K ? s[k] : 0.f;
+    const bool take = k < K && sc_k > thresh;
+    const unsigned bal = __ballot_sync(0xffffffffu, take);
+    if (take) {
+      const long long o = out0 + pos + __popc(bal & ((1u << lane) - 1u));
+      const float4 bx = reinterpret_cast<const float4*>(boxes + (long long)r * KB * 4)[KB == 1 ? 0 : k];
+      float4 cb;  // [D2] Boxes.clip: x in [0,w], y in [0,h]
+      cb.x = fminf(fmaxf(bx.x, 0.f), img_w);
+      cb.y = fminf(fmaxf(bx.y, 0.f), img_h);
+      cb.z = fminf(fmaxf(bx.z, 0.f), img_w);
+      cb.w = fminf(fmaxf(bx.w, 0.f), img_h);
+      cand_boxes[o] = cb;
+      cand_scores[o] = sc_k;
+      cand_roi[o] = rank;
+      cand_cls[o] = k;
+    }
+    pos += __popc(bal);
+  }
+}
+
 // ---------------------------------------------------------------------------------------- segmented NMS
 constexpr int NT = 1024;
 constexpr int SMEM_CAP = 4096;  // elements handled entirely in shared memory
@@ -808,16 +935,31 @@ int unit_box_get_deltas(const float* src, const float* tgt, float* deltas, int R
 
 int unit_detect_filter(const float* boxes, const float* probs, const int* roi_offsets, const float* image_hw,
                        int n_img, int R, int K, int KB, float score_thresh, float* cand_boxes, float* cand_scores,
-                       int* cand_roi, int* cand_cls, int* cand_counts, unit_stream_t stream) {
+                       int* cand_roi, int* cand_cls, int* cand_counts, void* workspace, size_t workspace_bytes,
+                       unit_stream_t stream) {
   UNIT_REQUIRE(n_img >= 0 && R >= 0 && K > 0 && (KB == K || KB == 1), "detect_filter: bad shape");
   if (n_img == 0) return UNIT_OK;
   UNIT_REQUIRE(roi_offsets && image_hw && cand_counts && (R == 0 || (boxes && probs && cand_boxes && cand_scores &&
                                                                       cand_roi && cand_cls)),
                "detect_filter: null pointer");
   UNIT_REQUIRE((((uintptr_t)boxes | (uintptr_t)cand_boxes) & 15) == 0, "detect_filter: boxes must be 16-byte aligned");
-  detect_filter_kernel<<<n_img, FT, 0, (cudaStream_t)stream>>>(boxes, probs, roi_offsets, image_hw, K, KB,
-                                                               score_thresh, (float4*)cand_boxes, cand_scores,
-                                                               cand_roi, cand_cls, cand_counts);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (workspace && workspace_bytes >= (size_t)R * 8 + 256 && R > 0 && !getenv("UNIT_FILTER_SINGLE")) {
+    // three small launches spread over the GPU (rows -> counts, per-image scans, rows -> candidates)
+    int* row_valid = (int*)workspace;
+    int* row_cnt = row_valid + R;
+    filter_count_kernel<<<cdiv(R, FW), FW * 32, 0, st>>>(boxes, probs, R, K, KB, score_thresh, row_valid, row_cnt);
+    UNIT_CHECK_LAUNCH("filter_count_kernel");
+    filter_scan_kernel<<<n_img, 1024, 0, st>>>(roi_offsets, row_valid, row_cnt, cand_counts);
+    UNIT_CHECK_LAUNCH("filter_scan_kernel");
+    filter_emit_kernel<<<cdiv(R, FW), FW * 32, 0, st>>>(boxes, probs, roi_offsets, image_hw, n_img, R, K, KB,
+                                                        score_thresh, row_valid, row_cnt, (float4*)cand_boxes,
+                                                        cand_scores, cand_roi, cand_cls);
+    UNIT_CHECK_LAUNCH("filter_emit_kernel");
+    return UNIT_OK;
+  }
+  detect_filter_kernel<<<n_img, FT, 0, st>>>(boxes, probs, roi_offsets, image_hw, K, KB, score_thresh,
+                                             (float4*)cand_boxes, cand_scores, cand_roi, cand_cls, cand_counts);
   UNIT_CHECK_LAUNCH("detect_filter_kernel");
   return UNIT_OK;
 }

@@ -335,17 +335,18 @@ def detect(boxes: torch.Tensor, probs: torch.Tensor, roi_offsets: torch.Tensor, 
     cand_roi = torch.empty((cap,), dtype=torch.int32, device=dev)
     cand_cls = torch.empty((cap,), dtype=torch.int32, device=dev)
     cand_counts = torch.empty((max(n_img, 1),), dtype=torch.int32, device=dev)
+    ws_bytes = lib().unit_nms_workspace_bytes(n_img, R * K)
+    ws = _workspace(dev, max(ws_bytes, R * 8 + 256))
     check(lib().unit_detect_filter(_ptr(boxes), _ptr(probs), _ptr(roi_offsets), _ptr(image_hw), n_img, R, K, KB,
                                    float(score_thresh), _ptr(cand_boxes), _ptr(cand_scores), _ptr(cand_roi),
-                                   _ptr(cand_cls), _ptr(cand_counts), _stream()), "unit_detect_filter")
+                                   _ptr(cand_cls), _ptr(cand_counts), _ptr(ws), ws.numel(), _stream()),
+          "unit_detect_filter")
     topk = int(topk) if topk >= 0 else cap
     det_boxes = torch.empty((n_img, topk, 4), dtype=_F32, device=dev)
     det_scores = torch.empty((n_img, topk), dtype=_F32, device=dev)
     det_classes = torch.empty((n_img, topk), dtype=torch.int64, device=dev)
     det_roi = torch.empty((n_img, topk), dtype=torch.int64, device=dev)
     det_counts = torch.empty((max(n_img, 1),), dtype=torch.int32, device=dev)
-    ws_bytes = lib().unit_nms_workspace_bytes(n_img, R * K)
-    ws = _workspace(dev, ws_bytes)
     check(lib().unit_detect_nms(_ptr(cand_boxes), _ptr(cand_scores), _ptr(cand_roi), _ptr(cand_cls),
                                 _ptr(cand_counts), _ptr(roi_offsets), n_img, R, K, float(nms_thresh), int(nms_mode),
                                 topk, _ptr(det_boxes), _ptr(det_scores), _ptr(det_classes), _ptr(det_roi),
