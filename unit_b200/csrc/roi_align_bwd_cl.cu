@@ -31,9 +31,12 @@ namespace cl {
 
 constexpr int P = 14;
 constexpr int CB = 64;                   // channels per work item (two per lane: l and l + 32)
-constexpr int CHUNK_ROWS = 2;            // bin rows per TMA tile
-constexpr int CHUNK_F = CHUNK_ROWS * P;  // 28 floats per channel and tile
-constexpr int NCHUNK = P / CHUNK_ROWS;   // 7
+#ifndef UNIT_BWD_ROWS
+#define UNIT_BWD_ROWS 2
+#endif
+constexpr int CHUNK_ROWS = UNIT_BWD_ROWS;  // bin rows per TMA tile (the last tile of a 4-row split is zero-filled past row 13)
+constexpr int CHUNK_F = CHUNK_ROWS * P;    // floats per channel and tile
+constexpr int NCHUNK = (P + CHUNK_ROWS - 1) / CHUNK_ROWS;
 #ifndef UNIT_BWD_NST
 #define UNIT_BWD_NST 2
 #endif
@@ -242,7 +245,7 @@ __device__ __forceinline__ bool build_axis(float start, float bin, int g, int si
 // Rare path (sampling grid > MAXG or a sample step > 1 cell): scalar taps straight from the staged tile.
 __device__ __noinline__ void direct_chunk(const Params& p, const WarpArea* wa, const float* tile, float* img, int k,
                                           int lane) {
-  for (int half = 0; half < CHUNK_ROWS; ++half) {
+  for (int half = 0; half < CHUNK_ROWS && CHUNK_ROWS * k + half < P; ++half) {
     const int ph = CHUNK_ROWS * k + half;
     for (int pw = 0; pw < P; ++pw) {
       const float gA = tile[lane * CHUNK_F + half * P + pw] * wa->inv_count;
@@ -382,7 +385,7 @@ roi_align_bwd_cl(const __grid_constant__ CUtensorMap gmap, const Params p) {
       int iy = 0, ph = 0, b = 0;
       for (int sy = 0; sy <= nsy; ++sy) {  // sample nsy: the zero sentinel that flushes the last row
         if (iy == 0 && ph < P) {
-          const int half = ph & 1;
+          const int half = ph % CHUNK_ROWS;
           if (half == 0) {
             b = cc % NST;
             mbar_wait(&wa->bar[b], (cc / NST) & 1u);
@@ -391,9 +394,9 @@ roi_align_bwd_cl(const __grid_constant__ CUtensorMap gmap, const Params p) {
           const float* ta = wa->stage[b] + lane * CHUNK_F + half * P;
 #pragma unroll
           for (int j = 0; j < P; ++j) g2[j] = pack2(ta[j], ta[j + 32 * CHUNK_F]);
-          if (half == 1) {
-            __syncwarp();  // every lane is done with the tile: refill the buffer two tiles ahead in the stream
-            if (lane == 0) refill(cur, nxt, ph >> 1, b);
+          if (half == CHUNK_ROWS - 1 || ph == P - 1) {
+            __syncwarp();  // every lane is done with the tile: refill the buffer NST tiles ahead in the stream
+            if (lane == 0) refill(cur, nxt, ph / CHUNK_ROWS, b);
           }
         }
         const ulonglong2 t = yt[sy];
