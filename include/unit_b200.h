@@ -213,6 +213,36 @@ int unit_mask_transfer(const float* logits, const float* s_seg, int s_is_2d, con
 int unit_mask_paste(const float* masks, const float* boxes, int D, int M, int img_h, int img_w, float threshold,
                     uint8_t* out, unit_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Weak-image training losses of the base stage.
+ * unit_mil_loss replaces WeakDetectorOutputsBase.losses, weak_detector_fast_rcnn.py:189-214:
+ *   per image i (rows img_offsets[i]..img_offsets[i+1]): x = softmax(cls_logits, classes) * softmax(det_logits,
+ *   proposals of the image); class_vector[i] = sum_r x; loss = multiplier * mean BCE(clamp(class_vector, 1e-6,
+ *   1 - 1e-6), gt_vector).  cls_logits / det_logits [R,K] (already divided by their temperatures), gt_vector [n_img,K]
+ *   in {0,1}.  Writes mil_scores [R,K] (= x, the first OICR supervision), class_vector [n_img,K], loss [1] and the
+ *   gradients d_cls, d_det [R,K] of loss (for upstream gradient 1).  workspace: n_img floats.
+ * unit_oicr_targets replaces compute_loss_inputs / get_proposal_clusters / label_and_sample_proposals
+ *   (:353-408, :308-351): for every class present in gt_vector (ascending == torch.unique order) pick the
+ *   image's not-yet-picked proposal with the largest probs[r, c] (first one on ties; picked rows count as 0
+ *   afterwards), match every proposal to those pseudo boxes with pairwise_iou + the UniT Matcher
+ *   (thresholds_host / labels_host as in unit_matcher), labels = class of the matched box | K (background) | -1
+ *   (ignore), weights = score of the matched box, 0 where the matched IoU < bg_threshold (if bg_threshold > 0).
+ *   probs [P_total, ld] row-major with ld >= K columns (ld = K for mil_scores, K+1 for a softmax of OICR scores).
+ *   pgt_index int64 [n_img,K]: image-local index of the proposal picked for class c, -1 if absent; pgt_scores
+ *   [n_img,K] its score.  Images without any present class get labels K and weights 0.
+ * unit_weighted_ce_loss replaces weighted_softmax_with_loss (:220-227): loss [1] = mean_r(weights[r] *
+ *   cross_entropy(scores[r], labels[r])), d_scores [R,K1] its gradient.  workspace: R floats. */
+int unit_mil_loss(const float* cls_logits, const float* det_logits, const int* img_offsets, const float* gt_vector,
+                  int n_img, int R, int K, float multiplier, float* mil_scores, float* class_vector, float* loss,
+                  float* d_cls, float* d_det, void* workspace, size_t workspace_bytes, unit_stream_t stream);
+int unit_oicr_targets(const float* probs, int ld, const float* prop_boxes, const int* prop_offsets,
+                      const float* gt_vector, int n_img, int P_total, int K, const float* thresholds_host,
+                      const int* labels_host, int T, float bg_threshold, int64_t* labels, float* weights,
+                      int64_t* pgt_index, float* pgt_scores, unit_stream_t stream);
+int unit_weighted_ce_loss(const float* scores, const int64_t* labels, const float* weights, int R, int K1,
+                          float* loss, float* d_scores, void* workspace, size_t workspace_bytes,
+                          unit_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

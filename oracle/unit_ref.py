@@ -206,3 +206,85 @@ def box_inference(scores: torch.Tensor, bbox: torch.Tensor, proposal_boxes: List
 
 
 UniTMatcher = MatcherWithVals  # modeling/matcher.py:54-98
+
+
+# ------------------------------------------------------------------------------------ weak-image training losses
+def mil_scores(cls_logits: torch.Tensor, det_logits: torch.Tensor, counts: Sequence[int]):
+    """weak_detector_fast_rcnn.py:202-210: per image, softmax over classes times softmax over the image's proposals;
+    returns (x [R,K], class_vectors [n_img,K])."""
+    xs, vecs = [], []
+    for c, d in zip(cls_logits.split(list(counts)), det_logits.split(list(counts))):
+        x = torch.softmax(c, -1) * torch.softmax(d, 0)
+        xs.append(x)
+        vecs.append(x.sum(0))
+    return torch.cat(xs, 0), torch.stack(vecs)
+
+
+def mil_loss(class_vectors: torch.Tensor, image_classes: Sequence[torch.Tensor], multiplier: float,
+             eps: float = 1e-6) -> torch.Tensor:
+    """weak_detector_fast_rcnn.py:211-216,247-250: BCE between the clamped class vector and the multi-hot labels."""
+    gt = torch.zeros_like(class_vectors)
+    for i, c in enumerate(image_classes):
+        gt[i, torch.unique(c)] = 1.0
+    return F.binary_cross_entropy(class_vectors.clamp(eps, 1 - eps), gt) * multiplier
+
+
+def oicr_targets(probs: torch.Tensor, boxes: Sequence[torch.Tensor], image_classes: Sequence[torch.Tensor],
+                 thresholds: Sequence[float], match_labels: Sequence[int], bg_threshold: float, num_classes: int):
+    """compute_loss_inputs (weak_detector_fast_rcnn.py:384-396) = get_proposal_clusters (:353-382) followed by
+    label_and_sample_proposals (:320-351).  Returns (labels i64 [R], cls_weights [R], picked: per image the index of
+    the proposal chosen for every unique class)."""
+    matcher = UniTMatcher(list(thresholds), list(match_labels), allow_low_quality_matches=False)
+    labels, weights, picked = [], [], []
+    start = 0
+    for b, cls in zip(boxes, image_classes):
+        p = probs[start:start + len(b)].clone()
+        start += len(b)
+        uniq = torch.unique(cls)
+        idxs, scores = [], []
+        for c in uniq.tolist():  # :358-365 -- best proposal of the class, then its whole row is zeroed
+            s, i = p[:, c].max(dim=0)
+            idxs.append(int(i))
+            scores.append(s)
+            p[int(i), :] = 0.0
+        picked.append(torch.tensor(idxs, dtype=torch.int64))
+        pseudo = b[idxs]
+        iou = pairwise_iou_tensor(pseudo, b)
+        matched_idxs, matched_labels, matched_vals = matcher(iou)
+        gt = uniq[matched_idxs].clone()  # :308-318
+        gt[matched_labels == 0] = num_classes
+        gt[matched_labels == -1] = -1
+        w = torch.stack(scores)[matched_idxs].clone()  # :392-396
+        if bg_threshold > 0.0:
+            w[matched_vals < bg_threshold] = 0.0
+        labels.append(gt)
+        weights.append(w)
+    return torch.cat(labels), torch.cat(weights), picked
+
+
+def pairwise_iou_tensor(b1: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
+    from .d2.structures import pairwise_iou
+    return pairwise_iou(Boxes(b1), Boxes(b2))
+
+
+def weak_losses(cls_logits: torch.Tensor, det_logits: torch.Tensor, oicr_scores: Sequence[torch.Tensor],
+                boxes: Sequence[torch.Tensor], image_classes: Sequence[torch.Tensor], thresholds=(0.5,),
+                match_labels=(0, 1), bg_threshold: float = 0.1, multiplier: float = 1.0):
+    """WeakDetectorOutputsBase.losses for TYPE == "OICR" without regression branches
+    (weak_detector_fast_rcnn.py:189-228).  cls_logits / det_logits are already divided by their temperatures."""
+    counts = [len(b) for b in boxes]
+    K = cls_logits.shape[1]
+    x, vecs = mil_scores(cls_logits, det_logits, counts)
+    out = {"loss_im_cls": mil_loss(vecs, image_classes, multiplier)}
+    sup = []
+    probs = x.detach()
+    for idx, score in enumerate(oicr_scores):
+        if idx > 0:
+            probs = torch.softmax(oicr_scores[idx - 1].detach(), dim=-1)
+        labels, weights, picked = oicr_targets(probs, boxes, image_classes, thresholds, match_labels, bg_threshold, K)
+        sup.append((labels, weights, picked))
+        if score.numel() > 0:  # :220-227
+            out["loss_oicr_{}".format(idx + 1)] = (F.cross_entropy(score, labels, reduction="none") * weights).mean()
+        else:
+            out["loss_oicr_{}".format(idx + 1)] = 0.0 * score.sum()
+    return out, sup

@@ -8,6 +8,8 @@ The fixtures pin oracle.unit_ref (and through it the CUDA path) to what the auth
   head_voc.pt       WSROIHeadNoMeta.forward end to end (pooler -> stand-in box head -> transfer -> NMS)
   mask_head.pt      mask_head.py MaskRCNNConvUpsampleHeadWithFineTune.forward (transfer + mask_rcnn_inference)
   weak_label.pt     weak_detector_fast_rcnn.py label_and_sample_proposals (pairwise_iou + UniT Matcher)
+  weak_losses.pt    weak_detector_fast_rcnn.py WeakDetectorOutputsBase.forward + losses (MIL + 3 OICR refinements),
+                    the per-iteration compute_loss_inputs outputs and the gradients of the summed loss
   glove_mean.pt     the reference's only shipped data fixture, re-saved as a bare tensor
 """
 from __future__ import annotations
@@ -226,6 +228,56 @@ def make_weak_label(ns):
     return out
 
 
+def make_weak_losses(ns):
+    cfg = shim.reference_cfg("VOC/VOC-RCNN-101-C4-split1.yaml", ["MODEL.ROI_HEADS.EMBEDDING_PATH", EMB])
+    wd = ns.weak.WeakDetectorOutputsBase(cfg, ShapeSpec(channels=D_FEAT))
+    randomize_(wd, 61, scale=0.35)
+    wd.train()
+    g = _seeded(62)
+    img = (600, 800)
+    counts = (96, 130, 64)
+    targets = [torch.tensor([3, 7, 3, 11]), torch.tensor([5]), torch.tensor([19, 0, 8, 8, 14])]
+    props = []
+    for n in counts:  # clusters of jittered copies so that many proposals overlap the picked boxes
+        seeds = boxes_in_image(8, img[0], img[1], g, 60.0)
+        b = boxes_in_image(n, img[0], img[1], g, 16.0)
+        k = n // 2
+        b[:k] = seeds[torch.randint(0, 8, (k,), generator=g)] + torch.randn(k, 4, generator=g) * 8
+        b[:, 0::2] = b[:, 0::2].clamp(0, img[1])
+        b[:, 1::2] = b[:, 1::2].clamp(0, img[0])
+        b[:, 2:] = torch.maximum(b[:, 2:], b[:, :2] + 4)
+        props.append(b[torch.randperm(n, generator=g)])
+    x = torch.randn(sum(counts), D_FEAT, generator=g).requires_grad_(True)
+    P = [Instances(img, proposal_boxes=Boxes(b), objectness_logits=torch.zeros(len(b))) for b in props]
+    preds, _ = wd(x)
+    cls_s, det_s, oicr_scores = preds[0], preds[1], preds[2]
+    losses = wd.losses(preds, P, targets)
+    total = sum(losses.values())
+    leaves = [cls_s, det_s, *oicr_scores]
+    grads = torch.autograd.grad(total, leaves + [x], retain_graph=True)
+    # the supervision every refinement classifier received (weak_detector_fast_rcnn.py:218-228)
+    import numpy as np
+    indices = np.insert(np.cumsum(counts), 0, 0)
+    uniq = [torch.unique(t) for t in targets]
+    with torch.no_grad():
+        mil = torch.cat([torch.softmax(c, -1) * torch.softmax(d, 0)
+                         for c, d in zip(cls_s.split(list(counts)), det_s.split(list(counts)))], 0)
+        sup = []
+        for idx in range(len(oicr_scores)):
+            probs = mil if idx == 0 else torch.softmax(oicr_scores[idx - 1].detach(), -1)
+            li = wd.compute_loss_inputs(P, probs.clone(), uniq, None, indices)
+            sup.append({"labels": li["labels"].clone(), "cls_weights": li["cls_weights"].clone()})
+    return {"state": {k: v.detach().clone() for k, v in wd.state_dict().items()}, "x": x.detach().clone(),
+            "image_size": img, "proposal_boxes": props, "targets": targets,
+            "bg_threshold": cfg.MODEL.ROI_HEADS.FAST_RCNN.WEAK_DETECTOR.BG_THRESHOLD,
+            "mil_multiplier": cfg.MODEL.ROI_HEADS.FAST_RCNN.WEAK_DETECTOR.MIL_MULTIPLIER,
+            "cls_stream": cls_s.detach().clone(), "det_stream": det_s.detach().clone(),
+            "oicr_scores": [o.detach().clone() for o in oicr_scores], "mil_scores": mil,
+            "losses": {k: v.detach().clone() for k, v in losses.items()}, "supervision": sup,
+            "grad_cls_stream": grads[0], "grad_det_stream": grads[1], "grad_oicr_scores": list(grads[2:5]),
+            "grad_x": grads[5]}
+
+
 def main():
     assert shim.reference_available(), "needs /root/reference"
     ns = shim.load_reference()
@@ -251,6 +303,7 @@ def main():
         "head_voc.pt": make_head_voc(ns),
         "mask_head.pt": make_mask_head(ns),
         "weak_label.pt": make_weak_label(ns),
+        "weak_losses.pt": make_weak_losses(ns),
     }
     only = set(sys.argv[1:])  # optional: regenerate just the named fixtures
     for name, obj in fixtures.items():

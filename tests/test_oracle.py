@@ -148,3 +148,24 @@ def test_reference_head_verbatim_matches_fixture():
         assert torch.allclose(fresh["det_scores"][i], gold["det_scores"][i], rtol=1e-5, atol=1e-7)
     fresh = make_golden.make_matcher(ns)
     assert torch.equal(fresh["rand_default"][0], load_golden("matcher.pt")["rand_default"][0])
+
+
+def test_unit_ref_weak_losses_fixture():
+    """MIL + OICR losses (weak_detector_fast_rcnn.py:189-228, 353-408) against the reference run verbatim: labels
+    bit-exact, loss weights / losses / gradients to fp32 round-off."""
+    gold = load_golden("weak_losses.pt")
+    cls_s = gold["cls_stream"].clone().requires_grad_(True)
+    det_s = gold["det_stream"].clone().requires_grad_(True)
+    oicr = [o.clone().requires_grad_(True) for o in gold["oicr_scores"]]
+    losses, sup = unit_ref.weak_losses(cls_s, det_s, oicr, gold["proposal_boxes"], gold["targets"],
+                                       bg_threshold=gold["bg_threshold"], multiplier=gold["mil_multiplier"])
+    assert set(losses) == set(gold["losses"])
+    for k, v in gold["losses"].items():
+        assert torch.allclose(losses[k], v, rtol=1e-6, atol=1e-8), k
+    for (labels, weights, _), g in zip(sup, gold["supervision"]):
+        assert torch.equal(labels, g["labels"])
+        assert torch.allclose(weights, g["cls_weights"], rtol=1e-6, atol=0)
+        assert (labels < 20).any() and (labels == 20).any() and (weights == 0).any()
+    grads = torch.autograd.grad(sum(losses.values()), [cls_s, det_s, *oicr])
+    for got, want in zip(grads, [gold["grad_cls_stream"], gold["grad_det_stream"], *gold["grad_oicr_scores"]]):
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-9)

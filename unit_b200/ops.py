@@ -316,6 +316,86 @@ def fastrcnn_loss(scores, deltas, proposals, gt_boxes, gt_classes, weights=(10.0
     return _FastRCNNLossFn.apply(scores, deltas, proposals, gt_boxes, gt_classes, tuple(weights), float(beta))
 
 
+# ---------------------------------------------------------------------------------- weak-image training losses
+class _MILLossFn(torch.autograd.Function):
+    """weak_detector_fast_rcnn.py:189-214 fused with its gradient: (loss_im_cls, mil_scores, class_vector)."""
+
+    @staticmethod
+    def forward(ctx, cls_logits, det_logits, img_offsets, gt_vector, multiplier):
+        dev = _need_cuda(cls_logits, det_logits, img_offsets, gt_vector)
+        cls_logits, det_logits = _c(cls_logits, _F32), _c(det_logits, _F32)
+        gt_vector = _c(gt_vector, _F32)
+        R, K = cls_logits.shape
+        n_img = img_offsets.numel() - 1
+        mil = torch.empty((R, K), dtype=_F32, device=dev)
+        class_vec = torch.empty((n_img, K), dtype=_F32, device=dev)
+        loss = torch.empty((1,), dtype=_F32, device=dev)
+        d_cls, d_det = torch.empty_like(mil), torch.empty_like(mil)
+        ws = _workspace(dev, max(n_img, 1) * 4)
+        check(lib().unit_mil_loss(_ptr(cls_logits), _ptr(det_logits), _ptr(img_offsets), _ptr(gt_vector), n_img, R, K,
+                                  float(multiplier), _ptr(mil), _ptr(class_vec), _ptr(loss), _ptr(d_cls), _ptr(d_det),
+                                  _ptr(ws), ws.numel(), _stream()), "unit_mil_loss")
+        ctx.save_for_backward(d_cls, d_det)
+        ctx.mark_non_differentiable(mil, class_vec)
+        return loss[0], mil, class_vec
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_mil, _g_vec):
+        d_cls, d_det = ctx.saved_tensors
+        return d_cls * g_loss, d_det * g_loss, None, None, None
+
+
+def mil_loss(cls_logits, det_logits, img_offsets, gt_vector, multiplier: float = 1.0):
+    """-> (loss_im_cls scalar, mil_scores [R,K] detached, class_vector [n_img,K] detached)."""
+    return _MILLossFn.apply(cls_logits, det_logits, img_offsets, gt_vector, float(multiplier))
+
+
+def oicr_targets(probs: torch.Tensor, prop_boxes: torch.Tensor, prop_offsets: torch.Tensor, gt_vector: torch.Tensor,
+                 thresholds: Sequence[float], labels: Sequence[int], bg_threshold: float):
+    """compute_loss_inputs (weak_detector_fast_rcnn.py:384-408) for every image in one launch.
+    -> labels i64 [P], cls_weights f32 [P], pgt_index i64 [n_img,K] (-1 = class absent), pgt_scores [n_img,K]."""
+    dev = _need_cuda(probs, prop_boxes, prop_offsets, gt_vector)
+    probs, prop_boxes, gt_vector = _c(probs, _F32), _c(prop_boxes, _F32), _c(gt_vector, _F32)
+    n_img, K = gt_vector.shape
+    Pt, ld = probs.shape
+    out_labels = torch.empty((Pt,), dtype=torch.int64, device=dev)
+    weights = torch.empty((Pt,), dtype=_F32, device=dev)
+    pgt_index = torch.empty((n_img, K), dtype=torch.int64, device=dev)
+    pgt_scores = torch.empty((n_img, K), dtype=_F32, device=dev)
+    thr, lab, T = _thr_arrays(thresholds, labels)
+    check(lib().unit_oicr_targets(_ptr(probs), ld, _ptr(prop_boxes), _ptr(prop_offsets), _ptr(gt_vector), n_img, Pt, K,
+                                  thr, lab, T, float(bg_threshold), _ptr(out_labels), _ptr(weights), _ptr(pgt_index),
+                                  _ptr(pgt_scores), _stream()), "unit_oicr_targets")
+    return out_labels, weights, pgt_index, pgt_scores
+
+
+class _WeightedCEFn(torch.autograd.Function):
+    """weighted_softmax_with_loss (weak_detector_fast_rcnn.py:220-227) fused with its gradient."""
+
+    @staticmethod
+    def forward(ctx, scores, labels, weights):
+        dev = _need_cuda(scores, labels, weights)
+        scores = _c(scores, _F32)
+        R, K1 = scores.shape
+        loss = torch.empty((1,), dtype=_F32, device=dev)
+        d_scores = torch.empty_like(scores)
+        ws = _workspace(dev, max(R, 1) * 4)
+        check(lib().unit_weighted_ce_loss(_ptr(scores), _ptr(_c(labels, torch.int64)), _ptr(_c(weights, _F32)), R, K1,
+                                          _ptr(loss), _ptr(d_scores), _ptr(ws), ws.numel(), _stream()),
+              "unit_weighted_ce_loss")
+        ctx.save_for_backward(d_scores)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_scores,) = ctx.saved_tensors
+        return d_scores * g, None, None
+
+
+def weighted_ce_loss(scores, labels, weights):
+    return _WeightedCEFn.apply(scores, labels, weights)
+
+
 NMS_CLASSWISE, NMS_COORD_TRICK, NMS_TV_CUDA_RULE, NMS_TV_CPU_RULE = 0, 1, 2, 3
 
 

@@ -70,20 +70,24 @@ class FusedSimilarity:
 class WeakDetectorOutputsBase(nn.Module):
     """OICR weak detector head (weak_detector_fast_rcnn.py:38-187).  In scope: ``evaluation`` (the mean of its three
     refinement classifiers is both the weak score and the source of the visual similarity), ``predict_*`` /
-    ``inference`` and ``label_and_sample_proposals``.  The MIL / OICR / PCL training losses are out of scope
-     and raise."""
+    ``inference``, ``label_and_sample_proposals`` and the MIL + OICR training ``losses`` (SURVEY.md section 8f rank 3;
+    the PCL variant with its proposal graph / KMeans and the regression branches stay out of scope and raise)."""
 
     @configurable
     def __init__(self, input_shape, *, box2box_transform, num_classes, cls_agnostic_bbox_reg=False, oicr_iter=3,
                  freeze_layers=(), detector_temp=1.0, classifier_temp=1.0, regression_branch=False,
                  proposal_matcher=None, test_score_thresh=0.0, test_nms_thresh=0.5, test_topk_per_image=100,
-                 oicr_regression_branch=False, base_classes=None, novel_classes=None, **unused):
+                 oicr_regression_branch=False, base_classes=None, novel_classes=None, fg_threshold=0.5,
+                 bg_threshold=0.1, mil_multiplier=4.0, weak_detector_type="OICR", **unused):
         super().__init__()
         if regression_branch or oicr_regression_branch or oicr_iter <= 0:
             raise NotImplementedError("only the shipped OICR configuration (OICR_ITER>0, no regression branches) "
                                       "is implemented (configs/default_config.py:40-50)")
         self.num_classes = num_classes
         self.oicr_iter = oicr_iter
+        self.fg_threshold, self.bg_threshold = fg_threshold, bg_threshold
+        self.mil_multiplier = mil_multiplier
+        self.weak_detector_type = weak_detector_type
         self.box_dim = len(box2box_transform.weights)
         self.num_bbox_reg_classes = 1 if cls_agnostic_bbox_reg else num_classes
         self.detector_temp, self.classifier_temp = detector_temp, classifier_temp
@@ -114,6 +118,10 @@ class WeakDetectorOutputsBase(nn.Module):
             "num_classes": cfg.MODEL.ROI_HEADS.NUM_CLASSES,
             "cls_agnostic_bbox_reg": cfg.MODEL.ROI_BOX_HEAD.CLS_AGNOSTIC_BBOX_REG,
             "oicr_iter": wd.OICR_ITER,
+            "fg_threshold": wd.FG_THRESHOLD,
+            "bg_threshold": wd.BG_THRESHOLD,
+            "mil_multiplier": wd.MIL_MULTIPLIER,
+            "weak_detector_type": wd.TYPE,
             "freeze_layers": cfg.MODEL.FREEZE_LAYERS.FAST_RCNN,
             "detector_temp": wd.DETECTOR_TEMP,
             "classifier_temp": wd.CLASSIFIER_TEMP,
@@ -163,9 +171,49 @@ class WeakDetectorOutputsBase(nn.Module):
             return [classifier_stream, detection_stream, oicr_scores, [], None, None], None
         return self.evaluation(x_weak)
 
+    def image_label_vector(self, weak_targets, dev) -> torch.Tensor:
+        """[n_img, K] with 1 at every class present in the image (weak_detector_fast_rcnn.py:203,213-216); its
+        non-zero columns in ascending order are the reference's ``torch.unique(gt_class)``."""
+        gt_vector = torch.zeros((len(weak_targets), self.num_classes), dtype=torch.float32, device=dev)
+        lens = [int(t.numel()) for t in weak_targets]
+        if sum(lens):
+            rows = torch.tensor([i for i, n in enumerate(lens) for _ in range(n)], dtype=torch.int64).to(dev)
+            cols = layers.cat([t.reshape(-1).to(dev).long() for t in weak_targets])
+            gt_vector[rows, cols] = 1.0
+        return gt_vector
+
+    def oicr_supervision(self, weak_predictions, weak_proposals, weak_targets):
+        """The (labels, cls_weights) pair ``compute_loss_inputs`` hands to every refinement classifier
+        (weak_detector_fast_rcnn.py:218-228, 384-396), plus the image-level MIL loss they start from."""
+        cls_stream, det_stream, oicr_scores = weak_predictions[0], weak_predictions[1], weak_predictions[2]
+        dev = cls_stream.device
+        offsets = ops.offsets_from_counts([len(p) for p in weak_proposals], dev)
+        boxes = layers.cat([p.proposal_boxes.tensor for p in weak_proposals])
+        gt_vector = self.image_label_vector(weak_targets, dev)
+        loss_im, probs, _ = ops.mil_loss(cls_stream, det_stream, offsets, gt_vector, self.mil_multiplier)
+        supervision = []
+        with torch.no_grad():
+            for idx in range(len(oicr_scores)):
+                if idx > 0:
+                    probs, _ = ops.softmax_decode(oicr_scores[idx - 1].detach(), None, None, want_boxes=False)
+                labels, weights, _, _ = ops.oicr_targets(probs, boxes, offsets, gt_vector,
+                                                         self.proposal_matcher.user_thresholds,
+                                                         self.proposal_matcher.labels, self.bg_threshold)
+                supervision.append((labels, weights))
+        return loss_im, supervision
+
     def losses(self, weak_predictions, weak_proposals, weak_targets):
-        raise NotImplementedError("MIL / OICR / PCL weak losses are outside the scoped RoI stage "
-                                  "(SURVEY.md section 2 row 3, section 8f rank 3)")
+        """weak_detector_fast_rcnn.py:189-245 for TYPE == "OICR": ``loss_im_cls`` (MIL) and ``loss_oicr_{1..n}``.
+        ``weak_targets``: one tensor of image-level class ids per image."""
+        if self.weak_detector_type != "OICR":
+            raise NotImplementedError("the PCL weak detector (proposal graph + KMeans, weak_detector_fast_rcnn.py:"
+                                      "410-519) is out of scope; WEAK_DETECTOR.TYPE is 'OICR' in every shipped YAML")
+        loss_im, supervision = self.oicr_supervision(weak_predictions, weak_proposals, weak_targets)
+        final_losses = {"loss_im_cls": loss_im}
+        for idx, (labels, weights) in enumerate(supervision):
+            final_losses["loss_oicr_{}".format(idx + 1)] = ops.weighted_ce_loss(weak_predictions[2][idx], labels,
+                                                                                weights)
+        return final_losses
 
     # -- inference (weak_detector_fast_rcnn.py:270-306) ---------------------------------------------------
     def predict_boxes(self, predictions, proposals):
@@ -310,9 +358,12 @@ class SupervisedDetectorOutputsBase(nn.Module):
         return (similarity is not None and not self.training), self.training, False
 
     def forward(self, x, novel_classes, base_classes, supervised_branch_x_weak=None, x_weak=None, similarity=None):
-        if x is None:
-            raise NotImplementedError("the weak-image-only branch (x is None) belongs to the out-of-scope MIL/OICR "
-                                      "training path")
+        if x is None:  # train_only_weak (fast_rcnn.py:393-397): zero supervised predictions, weak head only
+            scores = x_weak.new_zeros((x_weak.size(0), self.num_classes + 1))
+            bbox = x_weak.new_zeros((x_weak.size(0), self.num_classes * self.box_dim))
+            if self.training:
+                scores = scores.index_fill(1, novel_classes, float("-inf"))
+            return [scores, bbox], self.weak_detector_head(x_weak)[0]
         delta, pd, fts, ftd = self._linears(x)
         with torch.no_grad():
             weak_scores = self.weak_detector_head.mean_logits(x if supervised_branch_x_weak is None
@@ -351,10 +402,11 @@ class SupervisedDetectorOutputsBase(nn.Module):
     def losses(self, predictions, proposals, weak_predictions=None, weak_proposals=None, weak_targets=None,
                train_only_weak=False):
         """fast_rcnn.py:435-453: [D2] FastRCNNOutputs.losses (softmax CE + smooth-L1 on get_deltas)."""
+        final_losses = {}
         if weak_predictions is not None:
-            return self.weak_detector_head.losses(weak_predictions, weak_proposals, weak_targets)
+            final_losses.update(self.weak_detector_head.losses(weak_predictions, weak_proposals, weak_targets))
         if train_only_weak:
-            return {}
+            return final_losses
         scores, proposal_deltas = predictions
         if self.box_reg_loss_type != "smooth_l1":
             raise NotImplementedError("only the smooth_l1 box loss is used by the reference YAMLs")
@@ -363,7 +415,8 @@ class SupervisedDetectorOutputsBase(nn.Module):
         gt_boxes = layers.cat([p.gt_boxes.tensor for p in proposals])
         loss_cls, loss_box = ops.fastrcnn_loss(scores, proposal_deltas, prop, gt_boxes, gt_classes,
                                                self.box2box_transform.weights, self.smooth_l1_beta)
-        return {"loss_cls": loss_cls, "loss_box_reg": loss_box}
+        final_losses.update({"loss_cls": loss_cls, "loss_box_reg": loss_box})
+        return final_losses
 
     def predict_probs(self, predictions, proposals):
         scores, _ = predictions

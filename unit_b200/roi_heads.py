@@ -360,6 +360,16 @@ class WSROIHead(StandardROIHeads):
         n = self.batch_size_per_image // self.weak_divisor
         return [p[:n] for p in weak_proposals]
 
+    def _weak_box_features(self, weak_features, weak_proposals):
+        """Pooled + box-head features of the weakly labelled images (roi_heads.py:509-517)."""
+        if weak_features is None:
+            return None
+        feats = [weak_features[f] for f in self.box_in_features]
+        pooled = self.box_pooler(feats, [x.proposal_boxes for x in weak_proposals])
+        head = self.weak_box_head if self.weak_box_head is not None else self.box_head
+        x_weak = head(pooled)
+        return x_weak.mean(dim=[2, 3]) if x_weak.dim() > 2 else x_weak
+
     def _box_features(self, features, proposals):
         feats = [features[f] for f in self.box_in_features]
         pooled = self.box_pooler(feats, [x.proposal_boxes for x in proposals])
@@ -381,23 +391,29 @@ class WSROIHeadNoMeta(WSROIHead):
 
     def _forward_box(self, features, proposals, weak_features=None, weak_proposals=None, weak_targets=None, tta=False,
                      return_similarity=False, train_only_weak=False, return_proposals=False):
-        if train_only_weak or weak_features is not None:
-            raise NotImplementedError("the weak-image (MIL/OICR) training branch is out of scope "
-                                      "(SURVEY.md section 2 row 3)")
-        _, box_features, weak_branch = self._box_features(features, proposals)
-        x = box_features.mean(dim=[2, 3]) if box_features.dim() > 2 else box_features
+        x_weak = self._weak_box_features(weak_features, weak_proposals)
+        if train_only_weak:
+            if self.ALWAYS_TRANSFER or not self.training:
+                raise ValueError("train_only_weak needs a training head without base->novel transfer "
+                                 "(the reference dereferences box_features=None there, roi_heads.py:245-250)")
+            box_features, x, weak_branch = None, None, None
+        else:
+            _, box_features, weak_branch = self._box_features(features, proposals)
+            x = box_features.mean(dim=[2, 3]) if box_features.dim() > 2 else box_features
         similarity, sim_values = None, None
         if self.ALWAYS_TRANSFER or not self.training:
             if return_similarity:
                 similarity, sim_values = self.get_similarity_matrices(box_features, return_similarity=True)
             else:
                 similarity = self.get_similarity_matrices(box_features)
-        predictions, _ = self.box_predictor(x, supervised_branch_x_weak=weak_branch,
-                                            novel_classes=self._novel_classes_tensor,
-                                            base_classes=self._base_classes_tensor, x_weak=None,
-                                            similarity=similarity)
+        predictions, weak_predictions = self.box_predictor(x, supervised_branch_x_weak=weak_branch,
+                                                           novel_classes=self._novel_classes_tensor,
+                                                           base_classes=self._base_classes_tensor, x_weak=x_weak,
+                                                           similarity=similarity)
         if self.training:
-            losses = self.box_predictor.losses(predictions, proposals)
+            losses = self.box_predictor.losses(predictions, proposals, weak_predictions=weak_predictions,
+                                               weak_proposals=weak_proposals, weak_targets=weak_targets,
+                                               train_only_weak=train_only_weak)
             if self.train_on_pred_boxes:
                 raise NotImplementedError("TRAIN_ON_PRED_BOXES is False in every reference YAML")
             return losses, box_features, similarity
@@ -508,7 +524,7 @@ class WSROIHeadWithMaskFineTune(WSROIHeadNoMetaWithMask):
 
 @ROI_HEADS_REGISTRY.register()
 class WeakDetectorHead(StandardROIHeads):
-    """roi_heads.py:28-132: pool -> box head -> weak predictor; inference only (its MIL/OICR losses are out of scope)."""
+    """roi_heads.py:28-132: pool -> box head -> weak predictor (MIL + OICR losses in training)."""
 
     @configurable
     def __init__(self, *, box_in_features, box_pooler, box_head, box_predictor, freeze_layers=(), **kwargs):
@@ -541,11 +557,11 @@ class WeakDetectorHead(StandardROIHeads):
 
     def forward(self, images, features, proposals, targets=None, tta=False, **unused):
         del images
-        if self.training:
-            raise NotImplementedError("WeakDetectorHead training uses the out-of-scope MIL/OICR losses")
         feats = [features[f] for f in self.box_in_features]
         box_features = self.box_head(self.box_pooler(feats, [x.proposal_boxes for x in proposals]))
         predictions, _ = self.box_predictor(box_features)
+        if self.training:  # roi_heads.py:91-93,116-118: ``targets`` are the image-level class ids of each image
+            return proposals, dict(self.box_predictor.losses(predictions, proposals, targets))
         pred_instances, _ = self.box_predictor.inference(predictions, proposals, tta=tta)
         return pred_instances, {}
 
