@@ -159,10 +159,7 @@ class RoIStage:
         the graph's static outputs: they are overwritten by the next replay with the same key."""
         head = self.head
         head.move_mappings_to_gpu()
-        key = (features.data_ptr(), tuple(features.shape),
-               tuple(p.proposal_boxes.tensor.data_ptr() for p in proposals), tuple(len(p) for p in proposals),
-               tuple(t.gt_boxes.tensor.data_ptr() for t in targets), tuple(len(t) for t in targets),
-               tuple(t.gt_classes.data_ptr() for t in targets))
+        key = self._step_key(features, proposals, targets)
         st = self._graphs.get(key)
         if st is None:
             while len(self._graphs) >= self.max_graphs:  # callers that do not reuse buffers must not leak graphs
@@ -170,6 +167,28 @@ class RoIStage:
             st = _StepGraphs(self, features, proposals, targets, grad_pooled_fn)
             self._graphs[key] = st
         return st.run()
+
+    @staticmethod
+    def _step_key(features, proposals, targets):
+        return (features.data_ptr(), tuple(features.shape),
+                tuple(p.proposal_boxes.tensor.data_ptr() for p in proposals), tuple(len(p) for p in proposals),
+                tuple(t.gt_boxes.tensor.data_ptr() for t in targets), tuple(len(t) for t in targets),
+                tuple(t.gt_classes.data_ptr() for t in targets))
+
+    def prefetch_labels(self, features: torch.Tensor, proposals: List[Instances], targets: List[Instances],
+                        after: Optional[torch.cuda.Event] = None) -> bool:
+        """Start the labelling half of the NEXT ``train_step_graphed`` call on these buffers -- graph A and the read
+        of its fg/bg counts into pinned memory -- on a side stream, so that it overlaps the step that is running now.
+        Labelling depends only on proposals and ground truth (not on the weights), which is what makes this legal;
+        the ``randperm`` draw still happens inside ``train_step_graphed``, in call order, so sampled indices are the
+        ones the unpipelined sequence would draw.  The buffers must already hold the next batch, or ``after`` must be
+        an event that marks the end of their host->device copy.  They must not be the buffers of the step in flight.
+        Returns False (and does nothing) when this key has not been captured yet."""
+        st = self._graphs.get(self._step_key(features, proposals, targets))
+        if st is None or st._pending is not None:
+            return False
+        st.prefetch(after)
+        return True
 
 
 class _StepGraphs:
@@ -218,6 +237,14 @@ class _StepGraphs:
             self.grad_feat = stage._roi_backward(features, self.rois, self.pooled, grad_pooled_fn)
         self.launches += _lib.launch_count() - n0
         self._pending = draw  # the capture call is itself a step: its draw is replayed once by run()
+        # label prefetch (RoIStage.prefetch_labels): graph A on a side stream, counts into pinned memory
+        self._counts_pinned = torch.empty(tuple(self.lm.counts.shape), dtype=self.lm.counts.dtype).pin_memory()
+        self._counts_ready = torch.cuda.Event()
+        self._done = torch.cuda.Event()      # last step on these buffers has finished reading graph A's outputs
+        self._h2d_done = torch.cuda.Event()  # the draw's host buffer has been copied out
+        self._done.record(torch.cuda.current_stream(dev))
+        self._h2d_done.record(torch.cuda.current_stream(dev))
+        self._prefetched = False
 
     def _label(self):
         head = self.stage.head
@@ -239,12 +266,22 @@ class _StepGraphs:
 
     def run(self):
         stage = self.stage
+        main = torch.cuda.current_stream(self.features.device)
         if self._pending is not None:
             draw, self._pending = self._pending, None
         else:
-            self.graph_a.replay()
-            draw = self._draw(self.lm.counts.cpu().tolist())
+            if self._prefetched:  # graph A already ran on the label stream
+                self._prefetched = False
+                self._counts_ready.synchronize()
+                main.wait_event(self._counts_ready)
+                counts_h = self._counts_pinned.tolist()
+            else:
+                self.graph_a.replay()
+                counts_h = self.lm.counts.cpu().tolist()
+            self._h2d_done.synchronize()  # the previous draw has left the pinned buffer (normally long ago)
+            draw = self._draw(counts_h)
             self.devbuf.copy_(draw.host, non_blocking=True)
+            self._h2d_done.record(main)
         graphed = draw.sizes == self.sizes  # rare otherwise: fewer candidates than the batch size -> other shapes
         if graphed:
             self.graph_b.replay()
@@ -260,4 +297,19 @@ class _StepGraphs:
             grad_feat = stage._roi_backward(self.features, rois, pooled, self.grad_pooled_fn)
         if stage.bucket is not None:
             stage.bucket.finish(work)
+        self._done.record(main)
         return loss, grad_feat
+
+    def prefetch(self, after: Optional[torch.cuda.Event] = None):
+        stage = self.stage
+        side = stage.__dict__.get("_label_stream")
+        if side is None:
+            side = stage._label_stream = torch.cuda.Stream(device=self.features.device)
+        if after is not None:
+            side.wait_event(after)
+        side.wait_event(self._done)
+        with torch.cuda.stream(side):
+            self.graph_a.replay()
+            self._counts_pinned.copy_(self.lm.counts, non_blocking=True)
+            self._counts_ready.record(side)
+        self._prefetched = True
