@@ -51,6 +51,9 @@ unsigned long long unit_launch_count(void);
  * Backward writes grad_feat [N,C,H,W] completely (no pre-zeroing needed by the caller).
  */
 size_t unit_roi_align_workspace_bytes(int N, int C, int H, int W, int R, int dtype);
+/* [D2] poolers.convert_boxes_to_pooler_format (inside ROIPooler.forward): boxes [R,4] concatenated in image order +
+ * int32 prefix offsets [n_img+1] -> rois [R,5] = (image index, x1, y1, x2, y2). */
+int unit_boxes_to_rois(const float* boxes, const int* offsets, int n_img, int R, float* rois, unit_stream_t stream);
 int unit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, int C, int H, int W, int R, int PH,
                        int PW, float spatial_scale, int sampling_ratio, int aligned, int dtype, int rois_sorted,
                        void* workspace, size_t workspace_bytes, unit_stream_t stream);
@@ -179,6 +182,9 @@ typedef struct {
   int norm_cls, norm_bbox, norm_seg;
   int do_transfer, novel_neg_inf;
   int static_per_roi; /* bit h set: static_<head h> is [R,Nn,B] (an explicit per-RoI similarity) instead of [Nn,B] */
+  /* row strides (in floats) of delta_scores / proposal_deltas / ft_scores / ft_deltas, so that column blocks of one
+   * packed GEMM output can be passed without a copy; 0 = dense (K+1 resp. 4K) */
+  int ld_delta_scores, ld_proposal_deltas, ld_ft_scores, ld_ft_deltas;
 } unit_transfer_params;
 int unit_similarity_transfer(const unit_transfer_params* p, const float* vis_logits, const float* static_cls,
                              const float* static_bbox, const float* static_seg, const int* base, const int* novel,

@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from conftest import seeded
+from conftest import assert_close_rms, seeded
 
 pytestmark = pytest.mark.gpu
 
@@ -41,5 +41,6 @@ def test_linear_tf32_autograd():
     gy = torch.randn(256, 40, generator=g).cuda()
     y = ops.linear_tf32(x, w, b)
     y.backward(gy)
-    assert torch.allclose(w.grad, gy.t() @ x, rtol=1e-4, atol=1e-4)
+    # weight gradient: TF32 multiply / fp32 accumulate like the forward (north_star: tf32 transfer rel 1e-2)
+    assert_close_rms(w.grad.cpu(), (gy.t() @ x).cpu(), 1e-2, "d/dW of linear_tf32")
     assert torch.allclose(b.grad, gy.sum(0), rtol=1e-5, atol=1e-5)

@@ -521,6 +521,47 @@ def test_transfer_backward_matches_autograd_of_oracle(ops):
     assert_close_rms(p2.grad.cpu(), pd.grad, 1e-5, "grad proposal_deltas")
 
 
+def test_transfer_reads_packed_gemm_outputs_in_place(ops):
+    """Column blocks of packed GEMM outputs go in as (pointer, row stride); the fine-tune block as ONE packed tensor
+    with one packed gradient.  Same numbers, bit for bit, as the dense / separate-tensor call."""
+    g = seeded(92)
+    R, K = 50, 20
+    K1, K4 = K + 1, 4 * K
+    base = [0, 1, 3, 4, 6, 7, 8, 10, 11, 12, 14, 15, 16, 18, 19]
+    novel = [2, 5, 9, 13, 17]
+    dev = torch.device("cuda")
+    ling = torch.softmax(torch.randn(5, 15, generator=g), -1)
+    spec = ops.TransferSpec(K, base, novel, dev, {"cls": 0.5 * ling, "bbox": 0.5 * ling}, {"cls": 0.5, "bbox": 0.5},
+                            {"cls": 1, "bbox": 1}, 0.02)
+    vis = torch.randn(R, K1, generator=g).cuda()
+    y = torch.randn(R, K1 + K4 + 3, generator=g).cuda()       # [delta | bbox | padding]
+    yf = torch.randn(R, K1 + K4, generator=g).cuda()
+    ws = torch.randn(R, K1, generator=g).cuda()
+    gs, gb = torch.randn(R, K1, generator=g).cuda(), torch.randn(R, K4, generator=g).cuda()
+    for training in (False, True):
+        d1 = y[:, :K1].clone().requires_grad_(True)
+        p1 = y[:, K1:K1 + K4].clone().requires_grad_(True)
+        f1 = yf.clone().requires_grad_(True)
+        s1, b1 = ops.similarity_transfer(spec, vis, d1, p1, ws, f1[:, :K1], f1[:, K1:], True, training, False)
+        (s1.nan_to_num(neginf=0.0) * gs).sum().backward(retain_graph=True)
+        (b1 * gb).sum().backward()
+        y2 = y.clone().requires_grad_(True)
+        f2 = yf.clone().requires_grad_(True)
+        s2, b2 = ops.similarity_transfer(spec, vis, y2[:, :K1], y2[:, K1:K1 + K4], ws, None, None, True, training,
+                                         False, ft_packed=f2)
+        ((s2.nan_to_num(neginf=0.0) * gs).sum() + (b2 * gb).sum()).backward()
+        assert torch.equal(s1, s2) and torch.equal(b1, b2)
+        assert torch.equal(f1.grad, f2.grad)
+        assert torch.equal(d1.grad, y2.grad[:, :K1]) and torch.equal(p1.grad, y2.grad[:, K1:K1 + K4])
+        assert (y2.grad[:, K1 + K4:] == 0).all()
+    # frozen delta layers: no gradient is computed for them, the packed fine-tune gradient is unchanged
+    f3 = yf.clone().requires_grad_(True)
+    s3, b3 = ops.similarity_transfer(spec, vis, y[:, :K1], y[:, K1:K1 + K4], ws, None, None, True, True, False,
+                                     ft_packed=f3)
+    ((s3.nan_to_num(neginf=0.0) * gs).sum() + (b3 * gb).sum()).backward()
+    assert torch.equal(f3.grad, f2.grad)
+
+
 # ----------------------------------------------------------------------------------------------- masks
 def test_mask_transfer_and_paste_golden(ops):
     gold = load_golden("mask_head.pt")

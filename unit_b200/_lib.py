@@ -21,6 +21,7 @@ class TransferParams(Structure):
         ("wv_cls", c_float), ("wv_bbox", c_float), ("wv_seg", c_float),
         ("norm_cls", c_int), ("norm_bbox", c_int), ("norm_seg", c_int),
         ("do_transfer", c_int), ("novel_neg_inf", c_int), ("static_per_roi", c_int),
+        ("ld_delta_scores", c_int), ("ld_proposal_deltas", c_int), ("ld_ft_scores", c_int), ("ld_ft_deltas", c_int),
     ]
 
 
@@ -57,6 +58,7 @@ _SIGNATURES = {
     "unit_mask_paste": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, P, P]),
     "unit_predictor_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "unit_predictor_gemm": (c_int, [P, P, P, P, c_int, c_int, c_int, P, c_size_t, P]),
+    "unit_boxes_to_rois": (c_int, [P, P, c_int, c_int, P, P]),
     "unit_mil_loss": (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P, P, P, c_size_t, P]),
     "unit_oicr_targets": (c_int, [P, c_int, P, P, P, c_int, c_int, c_int, P, P, c_int, c_float, P, P, P, P, P]),
     "unit_weighted_ce_loss": (c_int, [P, P, P, c_int, c_int, P, P, P, c_size_t, P]),

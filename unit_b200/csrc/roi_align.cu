@@ -100,6 +100,24 @@ __global__ void roi_offsets_kernel(const float* __restrict__ rois, int R, int N,
   for (int n = prev + 1; n <= cur; ++n) off[n] = r;
 }
 
+// [D2] convert_boxes_to_pooler_format: rois[r] = (image of r, x1, y1, x2, y2) for boxes concatenated in image order
+__global__ void boxes_to_rois_kernel(const float4* __restrict__ boxes, const int* __restrict__ off, int n_img, int R,
+                                     float* __restrict__ rois) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  int lo = 0, hi = n_img;  // largest i with off[i] <= r
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= r) lo = mid; else hi = mid;
+  }
+  const float4 b = boxes[r];
+  float* o = rois + (long long)r * 5;
+  o[0] = (float)lo;
+  o[1] = b.x;
+  o[2] = b.y;
+  o[3] = b.z;
+  o[4] = b.w;
+}
 
 bool fwd_slab2_fits(int C, int H, int W, int dtype);
 int launch_fwd_slab2(const void* feat, const float* rois, void* out, int N, int C, int H, int W, int R, float scale,
@@ -175,6 +193,16 @@ int unit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, in
                                                                 N, C, H, W, total, PH, PW, spatial_scale,
                                                                 sampling_ratio, aligned);
   UNIT_CHECK_LAUNCH("roi_align_fwd_generic");
+  return UNIT_OK;
+}
+
+int unit_boxes_to_rois(const float* boxes, const int* offsets, int n_img, int R, float* rois, unit_stream_t stream) {
+  UNIT_REQUIRE(n_img >= 0 && R >= 0, "boxes_to_rois: bad shape");
+  if (R == 0) return UNIT_OK;
+  UNIT_REQUIRE(boxes && offsets && rois && n_img > 0, "boxes_to_rois: null pointer");
+  UNIT_REQUIRE(((uintptr_t)boxes & 15) == 0, "boxes_to_rois: boxes must be 16-byte aligned");
+  boxes_to_rois_kernel<<<cdiv(R, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)boxes, offsets, n_img, R, rois);
+  UNIT_CHECK_LAUNCH("boxes_to_rois_kernel");
   return UNIT_OK;
 }
 

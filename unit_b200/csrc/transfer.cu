@@ -91,8 +91,13 @@ __global__ void __launch_bounds__(TT) similarity_transfer_kernel(const TransferA
   __shared__ float s_red[2];
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = TT / 32;
 
-  for (int k = tid; k < K1; k += TT) s_delta[k] = a.delta_scores[(long long)r * K1 + k];
-  for (int k = tid; k < 4 * K; k += TT) s_pd[k] = a.proposal_deltas[(long long)r * 4 * K + k];
+  // row strides of the (possibly packed) GEMM outputs; 0 = dense
+  const long long ld_d = a.p.ld_delta_scores ? a.p.ld_delta_scores : K1;
+  const long long ld_p = a.p.ld_proposal_deltas ? a.p.ld_proposal_deltas : 4 * K;
+  const long long ld_fs = a.p.ld_ft_scores ? a.p.ld_ft_scores : K1;
+  const long long ld_fd = a.p.ld_ft_deltas ? a.p.ld_ft_deltas : 4 * K;
+  for (int k = tid; k < K1; k += TT) s_delta[k] = a.delta_scores[r * ld_d + k];
+  for (int k = tid; k < 4 * K; k += TT) s_pd[k] = a.proposal_deltas[r * ld_p + k];
 
   const bool need_v = a.p.do_transfer && (a.p.wv_cls != 0.f || a.p.wv_bbox != 0.f || a.p.wv_seg != 0.f);
   if (need_v) {
@@ -177,7 +182,7 @@ __global__ void __launch_bounds__(TT) similarity_transfer_kernel(const TransferA
     const int kind = k < K ? a.class_kind[k] : -1;
     if (a.p.do_transfer && kind >= NOVEL_TAG) v = v + s_tc[kind - NOVEL_TAG];
     if (a.weak_scores) v = v + a.weak_scores[(long long)r * K1 + k];
-    if (a.ft_scores) v = v + a.ft_scores[(long long)r * K1 + k];
+    if (a.ft_scores) v = v + a.ft_scores[r * ld_fs + k];
     if (a.p.novel_neg_inf && kind >= NOVEL_TAG) v = -INFINITY;
     a.out_scores[(long long)r * K1 + k] = v;
   }
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(TT) similarity_transfer_kernel(const TransferA
       if (kind >= NOVEL_TAG) v = s_tb[4 * (kind - NOVEL_TAG) + j];
       else if (kind < 0) v = 0.f;
     }
-    if (a.ft_deltas) v = v + a.ft_deltas[(long long)r * 4 * K + i];
+    if (a.ft_deltas) v = v + a.ft_deltas[r * ld_fd + i];
     a.out_bbox[(long long)r * 4 * K + i] = v;
   }
 }
@@ -387,6 +392,11 @@ int unit_similarity_transfer(const unit_transfer_params* p, const float* vis_log
   UNIT_REQUIRE(!need_v || vis_logits, "similarity_transfer: a head uses the visual term but vis_logits is NULL");
   UNIT_REQUIRE(!p->do_transfer || (base && novel) || (p->B == 0 && p->Nn == 0),
                "similarity_transfer: base/novel index arrays missing");
+  UNIT_REQUIRE((p->ld_delta_scores == 0 || p->ld_delta_scores >= p->K + 1) &&
+                   (p->ld_proposal_deltas == 0 || p->ld_proposal_deltas >= 4 * p->K) &&
+                   (p->ld_ft_scores == 0 || p->ld_ft_scores >= p->K + 1) &&
+                   (p->ld_ft_deltas == 0 || p->ld_ft_deltas >= 4 * p->K),
+               "similarity_transfer: a row stride is smaller than its row");
   TransferArgs a;
   a.p = *p;
   a.vis_logits = vis_logits;

@@ -19,9 +19,30 @@ from .structures import Boxes, Instances
 _SCALE_CLAMP = math.log(1000.0 / 16)
 
 
+def _adjacent_rows(tensors: List[torch.Tensor]) -> Optional[torch.Tensor]:
+    """The tensors as ONE view when they are consecutive row blocks of the same buffer (the per-image slices of a
+    flat kernel output, e.g. what ``sample_from_draw`` hands out), else None."""
+    first = tensors[0]
+    if first.requires_grad or not first.is_contiguous() or first.dim() == 0:
+        return None
+    base, rest = first.untyped_storage().data_ptr(), first.shape[1:]
+    nxt, rows = first.storage_offset(), 0
+    for t in tensors:
+        if (t.requires_grad or t.dtype != first.dtype or t.shape[1:] != rest or not t.is_contiguous()
+                or t.untyped_storage().data_ptr() != base or t.storage_offset() != nxt):
+            return None
+        nxt += t.numel()
+        rows += t.shape[0]
+    return first.as_strided((rows,) + tuple(rest), first.stride(), first.storage_offset())
+
+
 def cat(tensors: List[torch.Tensor], dim: int = 0) -> torch.Tensor:
     if len(tensors) == 1:
         return tensors[0]
+    if dim == 0:
+        view = _adjacent_rows(tensors)
+        if view is not None:
+            return view
     return torch.cat(tensors, dim)
 
 
@@ -66,8 +87,8 @@ class ROIPooler(torch.nn.Module):
         assert len(box_lists) == x[0].size(0), f"{len(box_lists)} box lists for batch {x[0].size(0)}"
         if len(box_lists) == 0:
             return torch.zeros((0, x[0].shape[1]) + self.output_size, device=x[0].device, dtype=x[0].dtype)
-        rois = cat([torch.cat((b.tensor.new_full((len(b), 1), float(i)), b.tensor), dim=1)
-                    for i, b in enumerate(box_lists)], dim=0)
+        rois = ops.boxes_to_rois(cat([b.tensor for b in box_lists]),
+                                 ops.offsets_from_counts([len(b) for b in box_lists], x[0].device))
         if len(self.scales) == 1:
             return ops.roi_align(x[0], rois, self.output_size, self.scales[0], self.sampling_ratio, self.aligned,
                                  rois_sorted=True)

@@ -89,6 +89,19 @@ def f32_const(values: Sequence[Sequence[float]], dev: torch.device) -> torch.Ten
     return t
 
 
+_ONES_CACHE = {}
+
+
+def _ones(n: int, dev: torch.device) -> torch.Tensor:
+    key = (int(n), str(dev))
+    t = _ONES_CACHE.get(key)
+    if t is None:
+        if len(_ONES_CACHE) >= 64:
+            _ONES_CACHE.clear()
+        t = _ONES_CACHE[key] = torch.ones(int(n), dtype=torch.float32, device=dev)
+    return t
+
+
 def offsets_from_counts(counts: Sequence[int], dev: torch.device) -> torch.Tensor:
     off = [0]
     for c in counts:
@@ -103,6 +116,17 @@ def _dtype_code(t: torch.Tensor) -> int:
     if t.dtype == torch.bfloat16:
         return _lib.UNIT_BF16
     raise RuntimeError(f"roi_align: unsupported dtype {t.dtype} (f32 and bf16 only)")
+
+
+def boxes_to_rois(boxes: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    """[D2] convert_boxes_to_pooler_format in one launch: [R,4] boxes in image order + int32 offsets -> [R,5] rois."""
+    dev = _need_cuda(boxes, offsets)
+    boxes = _c(boxes, _F32)
+    R = boxes.shape[0]
+    rois = torch.empty((R, 5), dtype=_F32, device=dev)
+    check(lib().unit_boxes_to_rois(_ptr(boxes), _ptr(offsets), offsets.numel() - 1, R, _ptr(rois), _stream()),
+          "unit_boxes_to_rois")
+    return rois
 
 
 def roi_align_forward(feat: torch.Tensor, rois: torch.Tensor, output_size: Tuple[int, int], spatial_scale: float,
@@ -521,15 +545,25 @@ def similarity_transfer_forward(spec: TransferSpec, vis_logits, delta_scores, pr
                                 want_similarity: Sequence[str] = ()):
     dev = _need_cuda(delta_scores, proposal_deltas)
     R = delta_scores.shape[0]
-    delta_scores, proposal_deltas = _c(delta_scores, _F32), _c(proposal_deltas, _F32)
+
+    def rows(t):  # column blocks of a packed GEMM output go in as (pointer, row stride): no copy
+        if t is None:
+            return None, 0
+        if t.dtype == _F32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+            return t, t.stride(0)
+        return _c(t, _F32), 0
+
+    (delta_scores, ld_d), (proposal_deltas, ld_p) = rows(delta_scores), rows(proposal_deltas)
+    (ft_scores, ld_fs), (ft_deltas, ld_fd) = rows(ft_scores), rows(ft_deltas)
     cv = lambda t: None if t is None else _c(t, _F32)
-    vis_logits, weak_scores, ft_scores, ft_deltas = cv(vis_logits), cv(weak_scores), cv(ft_scores), cv(ft_deltas)
-    out_scores = torch.empty_like(delta_scores)
-    out_bbox = torch.empty_like(proposal_deltas)
+    vis_logits, weak_scores = cv(vis_logits), cv(weak_scores)
+    out_scores = torch.empty(tuple(delta_scores.shape), dtype=_F32, device=dev)
+    out_bbox = torch.empty(tuple(proposal_deltas.shape), dtype=_F32, device=dev)
     sims = {h: (torch.empty((R, spec.Nn, spec.B), dtype=_F32, device=dev) if h in want_similarity else None)
             for h in ("cls", "bbox", "seg")}
     if R:
         p = spec.params(R, do_transfer, novel_neg_inf)
+        p.ld_delta_scores, p.ld_proposal_deltas, p.ld_ft_scores, p.ld_ft_deltas = ld_d, ld_p, ld_fs, ld_fd
         check(lib().unit_similarity_transfer(ctypes.byref(p), _ptr(vis_logits), _ptr(spec.static.get("cls")),
                                              _ptr(spec.static.get("bbox")), _ptr(spec.static.get("seg")),
                                              _ptr(spec.base_i32), _ptr(spec.novel_i32), _ptr(spec.class_kind),
@@ -564,8 +598,13 @@ class _TransferFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, vis_logits, delta_scores, proposal_deltas, weak_scores, ft_scores, ft_deltas, do_transfer,
-                novel_neg_inf, detach_transfer):
+                novel_neg_inf, detach_transfer, ft_packed=None):
         need_grad = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        ctx.need_delta_grad = need_grad
+        ctx.ft_is_packed = ft_packed is not None
+        if ft_packed is not None:  # [R, (K+1) + 4K]: both fine-tune blocks of one GEMM output, one gradient tensor
+            K1 = delta_scores.shape[1]
+            ft_scores, ft_deltas = ft_packed[:, :K1], ft_packed[:, K1:]
         want = ("cls", "bbox") if (need_grad and do_transfer and not detach_transfer) else ()
         out_scores, out_bbox, sims = similarity_transfer_forward(spec, vis_logits, delta_scores, proposal_deltas,
                                                                  weak_scores, ft_scores, ft_deltas, do_transfer,
@@ -583,24 +622,29 @@ class _TransferFn(torch.autograd.Function):
             kind = ctx.spec.class_kind
             g_scores = g_scores.clone()
             g_scores[:, :-1][:, kind >= NOVEL_TAG] = 0
-        if ctx.do_transfer:
+        if not ctx.need_delta_grad:  # frozen delta layers (fine-tuning): nothing flows through the transfer
+            g_delta = g_pd = None
+        elif ctx.do_transfer:
             s_cls, s_bbox = (saved[0], saved[1]) if len(saved) == 2 else (None, None)
             g_delta, g_pd = similarity_transfer_backward(ctx.spec, s_cls, s_bbox, g_scores, g_bbox,
                                                          detach_transfer=ctx.detach or s_cls is None)
         else:
             g_delta, g_pd = g_scores, g_bbox
+        if ctx.ft_is_packed:
+            return (None, None, g_delta, g_pd, None, None, None, None, None, None,
+                    torch.cat([g_scores, g_bbox], 1))
         return (None, None, g_delta, g_pd, None, g_scores if ctx.has_ft[0] else None,
-                g_bbox if ctx.has_ft[1] else None, None, None, None)
+                g_bbox if ctx.has_ft[1] else None, None, None, None, None)
 
 
 def similarity_transfer(spec: TransferSpec, vis_logits, delta_scores, proposal_deltas, weak_scores=None,
                         ft_scores=None, ft_deltas=None, do_transfer=True, novel_neg_inf=False,
-                        detach_transfer=False):
+                        detach_transfer=False, ft_packed=None):
     if vis_logits is not None and vis_logits.requires_grad:
         raise RuntimeError("similarity_transfer: gradients through the visual similarity are not implemented "
                            "(it is computed from frozen weights in every shipped fine-tune config)")
     return _TransferFn.apply(spec, vis_logits, delta_scores, proposal_deltas, weak_scores, ft_scores, ft_deltas,
-                             bool(do_transfer), bool(novel_neg_inf), bool(detach_transfer))
+                             bool(do_transfer), bool(novel_neg_inf), bool(detach_transfer), ft_packed)
 
 
 # ------------------------------------------------------------------------------------------------- predictor GEMM
@@ -622,7 +666,7 @@ def predictor_gemm_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torc
 
 
 class _LinearTF32Fn(torch.autograd.Function):
-    """Forward on the hand-written tcgen05 GEMM; the weight/bias gradients are plain library GEMMs (cuBLAS)."""
+    """Forward on the hand-written tcgen05 GEMM; the weight/bias gradients are plain library GEMMs (cuBLAS, TF32)."""
 
     @staticmethod
     def forward(ctx, x, w, bias):
@@ -633,9 +677,17 @@ class _LinearTF32Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
-        gx = gy @ w if ctx.needs_input_grad[0] else None
-        gw = gy.t() @ x if ctx.needs_input_grad[1] else None
-        gb = gy.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        # same precision contract as the forward (TF32 multiply, fp32 accumulate; north_star: transfer rel 1e-2)
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            gx = gy @ w if ctx.needs_input_grad[0] else None
+            gw = gy.t() @ x if ctx.needs_input_grad[1] else None
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+        gb = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:  # column sums as one fp32 gemv instead of a strided reduction
+            gb = torch.mv(gy.t(), _ones(gy.shape[0], gy.device))
         return gx, gw, gb
 
 

@@ -325,7 +325,8 @@ class SupervisedDetectorOutputsBase(nn.Module):
         return None, None
 
     def _linears(self, x: torch.Tensor):
-        """One packed GEMM for every Linear that reads ``x``: [delta | bbox | (ft cls | ft bbox)]."""
+        """One packed GEMM for every Linear that reads ``x``: [delta | bbox | (ft cls | ft bbox)].  Returns column
+        views (delta, bbox, packed fine-tune block or None); the transfer kernel reads them in place (row strides)."""
         K1, K4 = self.num_classes + 1, self.num_classes * self.box_dim
         base = [self.cls_score_delta.weight, self.bbox_pred_delta.weight, self.cls_score_delta.bias,
                 self.bbox_pred_delta.bias]
@@ -341,17 +342,13 @@ class SupervisedDetectorOutputsBase(nn.Module):
             y = _linear(x, cached[1], cached[2], self.gemm_precision)
             yf = _linear(x, torch.cat([ft_c.weight, ft_b.weight], 0), torch.cat([ft_c.bias, ft_b.bias], 0),
                          self.gemm_precision)
-            return y[:, :K1], y[:, K1:], yf[:, :K1], yf[:, K1:]
+            return y[:, :K1], y[:, K1:], yf
         ws, bs = base[:2], base[2:]
         if ft_c is not None:
             ws = ws + [ft_c.weight, ft_b.weight]
             bs = bs + [ft_c.bias, ft_b.bias]
         y = _linear(x, torch.cat(ws, 0), torch.cat(bs, 0), self.gemm_precision)
-        delta, pd = y[:, :K1], y[:, K1:K1 + K4]
-        fts = ftd = None
-        if ft_c is not None:
-            fts, ftd = y[:, K1 + K4:2 * K1 + K4], y[:, 2 * K1 + K4:]
-        return delta, pd, fts, ftd
+        return y[:, :K1], y[:, K1:K1 + K4], (y[:, K1 + K4:] if ft_c is not None else None)
 
     def _transfer_mode(self, similarity):
         """(do_transfer, novel_neg_inf, detach) for this predictor kind (fast_rcnn.py:401,427-428)."""
@@ -364,14 +361,14 @@ class SupervisedDetectorOutputsBase(nn.Module):
             if self.training:
                 scores = scores.index_fill(1, novel_classes, float("-inf"))
             return [scores, bbox], self.weak_detector_head(x_weak)[0]
-        delta, pd, fts, ftd = self._linears(x)
+        delta, pd, ft_packed = self._linears(x)
         with torch.no_grad():
             weak_scores = self.weak_detector_head.mean_logits(x if supervised_branch_x_weak is None
                                                               else supervised_branch_x_weak)
         do_transfer, neg_inf, detach = self._transfer_mode(similarity)
         spec, vis_logits = self._resolve_similarity(similarity, base_classes, novel_classes, x.device)
-        scores, bbox = ops.similarity_transfer(spec, vis_logits, delta, pd, weak_scores, fts, ftd, do_transfer,
-                                               neg_inf, detach)
+        scores, bbox = ops.similarity_transfer(spec, vis_logits, delta, pd, weak_scores, None, None, do_transfer,
+                                               neg_inf, detach, ft_packed=ft_packed)
         weak_branch_return = None
         if x_weak is not None:
             weak_branch_return, _ = self.weak_detector_head(x_weak)
