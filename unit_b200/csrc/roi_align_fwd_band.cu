@@ -29,7 +29,10 @@ using v2::CS;
 using v2::P;
 using v2::Params;
 constexpr int NQ = CS / 4;   // channel quads per slab
-constexpr int NW = 12;
+#ifndef UNIT_FWD_NW
+#define UNIT_FWD_NW 12
+#endif
+constexpr int NW = UNIT_FWD_NW;
 constexpr int NT = NW * 32;
 constexpr int MAXB = 8;      // band columns per bin: sampling grid <= 7 with unit sample steps
 constexpr int MAXGY = 8;
@@ -48,7 +51,9 @@ static_assert(sizeof(RoiTab) == 1536, "RoiTab layout");
 
 template <typename T>
 struct __align__(128) WarpArea {
+#ifndef UNIT_FWD_DIRECT  // experiment: lanes store straight to global memory, no staging block (more warps fit)
   T stage[CS * P * P];
+#endif
   RoiTab tab;
   uint64_t bar;
 };
@@ -354,7 +359,9 @@ __global__ void __launch_bounds__(NT, 1) roi_align_fwd_band(const Params p, cons
   const int wl = writer ? lane : 2 * P - 1;
   const int half = wl >= P ? 1 : 0, pw = wl - half * P;
   const float4* quad = slab + (size_t)half * qs;
+#ifndef UNIT_FWD_DIRECT
   T* stage_lane = wa->stage + (4 * half) * (P * P) + pw;
+#endif
   uint32_t parity = 0;
 
   for (int i = tid; i < NQ * (qs - HW); i += NT) {
@@ -418,8 +425,12 @@ __global__ void __launch_bounds__(NT, 1) roi_align_fwd_band(const Params p, cons
       __syncwarp();  // the table buffer is free: fetch the next RoI and start loading its table
       const int nxt = fetch();
       if (nxt < r1) issue_tab(nxt);
+#ifndef UNIT_FWD_DIRECT
       if (lane == 0) v2::bulk_wait_read_all();  // the previous bulk store has drained this warp's staging block
       __syncwarp();
+#else
+      T* stage_lane = out + ((long long)(r_base + cur) * p.C + (long long)k * CS + 4 * half) * (P * P) + pw;
+#endif
       if (!(p.debug & 1)) {
         if (mode == 1) {
           const float4* rowp = quad + (size_t)y0 * p.W + bx;
@@ -436,6 +447,7 @@ __global__ void __launch_bounds__(NT, 1) roi_align_fwd_band(const Params p, cons
           }
         }
       }
+#ifndef UNIT_FWD_DIRECT
       v2::fence_async_smem();
       __syncwarp();
       if (lane == 0 && !(p.debug & 2)) {
@@ -443,11 +455,14 @@ __global__ void __launch_bounds__(NT, 1) roi_align_fwd_band(const Params p, cons
                        (uint32_t)(CS * P * P * sizeof(T)));
         v2::bulk_commit();
       }
+#endif
       cur = nxt;
     }
     u = seg_end_u;
   }
+#ifndef UNIT_FWD_DIRECT
   if (lane == 0) v2::bulk_wait_all();
+#endif
 }
 
 template <typename T>
