@@ -87,6 +87,28 @@ def test_roi_align_bf16_io(ops):
     assert (err <= 2 ** -8 * ref.abs() + 1e-6).all(), err.max()
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 50, 84, 96, 0), (1, 128, 20, 30, 40, 2), (3, 192, 7, 9, 10, 0)])
+def test_roi_align_backward_channel_lane_bf16(ops, shape):
+    """bf16 grad_out / grad_feat through the channel-lane backward (pair-view TMA tiles): fp32 accumulation, ONE bf16
+    rounding of the result."""
+    n, c, h, w, per, sr = shape
+    g = seeded(350 + c + h)
+    rois = _rois(n, per, h * 16, w * 16, g)
+    rois[0, 1:] = torch.tensor([-40.0, -30.0, 100.0, 90.0])
+    rois[1, 1:] = torch.tensor([0.0, 0.0, w * 16.0, h * 16.0])                 # whole image -> direct path
+    rois[2, 1:] = torch.tensor([33.0, 47.0, 33.0, 47.0])                       # zero-size
+    rois[3, 1:] = torch.tensor([-500.0, -500.0, -100.0, -100.0])               # entirely outside
+    rois = rois[torch.randperm(rois.shape[0], generator=g)]
+    gout = torch.randn(rois.shape[0], c, 14, 14, generator=g).bfloat16()
+    ref = torch.ops.torchvision._roi_align_backward(gout.float(), rois, 1.0 / 16, 14, 14, n, c, h, w, sr, True)
+    mag = torch.ops.torchvision._roi_align_backward(gout.float().abs(), rois, 1.0 / 16, 14, 14, n, c, h, w, sr, True)
+    got = ops.roi_align_backward(gout.cuda(), rois.cuda(), (n, c, h, w), 1.0 / 16, sr, True, False)
+    assert got.dtype == torch.bfloat16
+    err = (got.float().cpu() - ref).abs()
+    assert (err <= 2 ** -8 * ref.abs() + 1e-5 * mag + 1e-30).all(), err.max()
+    assert ref.abs().max() > 0
+
+
 @pytest.mark.parametrize("shape", [(2, 32, 50, 84, 64), (1, 8, 13, 17, 21)])
 def test_roi_align_backward_matches_torchvision(ops, shape):
     n, c, h, w, per = shape

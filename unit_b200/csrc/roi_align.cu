@@ -133,7 +133,7 @@ int launch_bwd_slab2(const void* gout, const float* rois, void* gfeat, void* f32
 
 bool bwd_cl_fits(int C, int H, int W, int R, int dtype, const void* gout);
 int launch_bwd_cl(const void* gout, const float* rois, void* gfeat, void* ws, int N, int C, int H, int W, int R,
-                  float scale, int sr, int aligned, cudaStream_t st);
+                  float scale, int sr, int aligned, int dtype, cudaStream_t st);
 
 static size_t offsets_bytes(int N) { return ((size_t)(N + 2) * sizeof(int) + 255) / 256 * 256; }
 
@@ -226,7 +226,7 @@ int unit_roi_align_bwd(const void* grad_out, const float* rois, void* grad_feat,
       return UNIT_EWORKSPACE;
     }
     return launch_bwd_cl(grad_out, rois, grad_feat, (char*)workspace + offsets_bytes(N), N, C, H, W, R, spatial_scale,
-                         sampling_ratio, aligned, st);
+                         sampling_ratio, aligned, dtype, st);
   }
   if (rois_sorted && PH == 14 && PW == 14 && bwd_slab2_fits(C, H, W, dtype) && (((uintptr_t)grad_out) & 15) == 0) {
     const size_t need = offsets_bytes(N) + bwd_slab2_workspace_bytes(N, C, H, W, dtype);

@@ -1,4 +1,4 @@
-// ROIAlign backward, channel-lane kernel (fp32, C % 64 == 0, 14 x 14 bins).
+// ROIAlign backward, channel-lane kernel (fp32 or bf16 I/O, C % 64 == 0, 14 x 14 bins).
 //
 // The gradient of one RoI is separable:  dF[c][y][x] = sum_ph sum_pw Wy[ph][y] * g[c][ph][pw] * Wx[pw][x], with the SAME
 // Wy / Wx for every channel.  So a lane owns CHANNELS (two of them), and the whole warp executes one warp-uniform
@@ -16,9 +16,14 @@
 //               lower tap column advances, `cur` is complete: ONE red.global.add.v2.f32 per (cell, lane), 256
 //               contiguous bytes per warp, into a channel-last fp32 image of grad_feat that lives in L2.
 //   epilogue    a tiled transpose turns the channel-last image into NCHW.
+//   bf16 I/O    grad_out rows are 392 bytes, not a legal TMA stride, so the tensor map views channel PAIRS (784-byte
+//               rows of 2 x 196 bf16) cut into seven 112-byte boxes that arrive through a 4-slot ring (see BF_*
+//               below); lane l owns channels 2l and 2l+1, accumulation and the L2 image stay fp32, the transpose
+//               rounds to bf16 once.
 // Exactly one vector reduction per (RoI, footprint cell, channel pair) replaces torchvision's 4 * gh * gw scalar atomics
 // per output element (roi_align_kernel.cu, bilinear_interpolate_gradient + atomicAdd).
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -36,7 +41,6 @@ constexpr int CB = 64;                   // channels per work item (two per lane
 #endif
 constexpr int CHUNK_ROWS = UNIT_BWD_ROWS;  // bin rows per TMA tile (the last tile of a 4-row split is zero-filled past row 13)
 constexpr int CHUNK_F = CHUNK_ROWS * P;    // floats per channel and tile
-constexpr int NCHUNK = (P + CHUNK_ROWS - 1) / CHUNK_ROWS;
 #ifndef UNIT_BWD_NST
 #define UNIT_BWD_NST 2
 #endif
@@ -49,13 +53,32 @@ constexpr int NT = NW * 32;
 constexpr int MAXG = 6;                  // sampling grid with tables: RoI side <= 84 feature cells (1344 px at 1/16)
 constexpr int MAXS = P * MAXG;
 constexpr uint32_t TILE_BYTES = CB * CHUNK_F * sizeof(float);
+// bf16 I/O: the tensor map views channel PAIRS (rows of 2 x 196 bf16 = 784 B); a pair row is exactly 7 boxes of 56
+// elements (112 B, every box start 16-byte aligned): boxes 0-2 = bin rows 0-11 of the even channel, box 3 = its rows
+// 12-13 followed by rows 0-1 of the odd channel, boxes 4-6 = rows 2-13 of the odd channel.  A warp walks the bin rows in
+// 7 steps of two; step s needs the boxes (E, O) = (0,3) (0,4) (1,4) (1,5) (2,5) (2,6) (3,6).  They arrive in the order
+// 0 3 4 1 5 2 6 3 (box 3 twice) into a ring of 4 slots: arrival a -> slot a & 3, mbarrier parity (a >> 2) & 1.
+constexpr int BF_BOX_ELEMS = 4 * P;                          // 56
+constexpr uint32_t BF_BOX_BYTES = (CB / 2) * BF_BOX_ELEMS * 2;  // 3584: 32 channel pairs x 112 B
+constexpr int BF_PITCH = BF_BOX_ELEMS * 2;                   // bytes per channel pair and box
+constexpr int BF_SLOTS = 4;
+static_assert(BF_SLOTS * BF_BOX_BYTES <= NST * TILE_BYTES, "the bf16 ring must fit the staging buffers");
+constexpr int NBAR = NST > BF_SLOTS ? NST : BF_SLOTS;
+template <bool BF>
+struct Tile {
+  static constexpr int ROWS = BF ? 2 : CHUNK_ROWS;
+  static constexpr int NCH = (P + ROWS - 1) / ROWS;
+};
+__device__ __forceinline__ int bf_box(int a) { return (0x36251430u >> (4 * a)) & 7; }     // arrival -> box
+__device__ __forceinline__ int bf_slot_even(int s) { return (0x3113300u >> (4 * s)) & 7; }  // step -> slot of E
+__device__ __forceinline__ int bf_slot_odd(int s) { return (0x2200221u >> (4 * s)) & 7; }   // step -> slot of O
 
 struct __align__(128) WarpArea {
   float stage[NST][CB * CHUNK_F];
   float4 xt[MAXS];  // (hx / count, hx / count, lx / count, lx / count)
   float4 yt[MAXS + 4];  // (hy, hy, ly, ly); entry 14*gh is a zero sentinel whose advance bit is set
   uint32_t xadv[4], yadv[4];  // bit s: sample s is the last one whose lower tap is its cell (window advances after it)
-  uint64_t bar[NST];
+  uint64_t bar[NBAR];
   int x0, y0, gw, gh, mode;
   float inv_count, start_w, start_h, bin_w, bin_h;
 };
@@ -243,27 +266,27 @@ __device__ __forceinline__ bool build_axis(float start, float bin, int g, int si
 }
 
 // Rare path (sampling grid > MAXG or a sample step > 1 cell): scalar taps straight from the staged tile.
-__device__ __noinline__ void direct_chunk(const Params& p, const WarpArea* wa, const float* tile, float* img, int k,
-                                          int lane) {
-  for (int half = 0; half < CHUNK_ROWS && CHUNK_ROWS * k + half < P; ++half) {
-    const int ph = CHUNK_ROWS * k + half;
-    for (int pw = 0; pw < P; ++pw) {
-      const float gA = tile[lane * CHUNK_F + half * P + pw] * wa->inv_count;
-      const float gB = tile[(lane + 32) * CHUNK_F + half * P + pw] * wa->inv_count;
-      for (int iy = 0; iy < wa->gh; ++iy) {
-        int ylo, yhi;
-        float ly, hy;
-        const bool vy = axis_tap(sample_coord(wa->start_h, wa->bin_h, ph, iy, wa->gh), p.H, ylo, yhi, ly, hy);
-        for (int ix = 0; ix < wa->gw; ++ix) {
-          int xlo, xhi;
-          float lx, hx;
-          const bool vx = axis_tap(sample_coord(wa->start_w, wa->bin_w, pw, ix, wa->gw), p.W, xlo, xhi, lx, hx);
-          if (vy && vx) {
-            red2(reinterpret_cast<char*>(img + ((size_t)ylo * p.W + xlo) * p.C), pack2(gA * hy * hx, gB * hy * hx));
-            red2(reinterpret_cast<char*>(img + ((size_t)ylo * p.W + xhi) * p.C), pack2(gA * hy * lx, gB * hy * lx));
-            red2(reinterpret_cast<char*>(img + ((size_t)yhi * p.W + xlo) * p.C), pack2(gA * ly * hx, gB * ly * hx));
-            red2(reinterpret_cast<char*>(img + ((size_t)yhi * p.W + xhi) * p.C), pack2(gA * ly * lx, gB * ly * lx));
-          }
+// Rare path (sampling grid > MAXG or a sample step > 1 cell): scalar taps of one bin row, straight from the staged
+// tile.  ta / tb: the row's 14 values of the lane's two channels (fp32 or bf16).
+template <typename E>
+__device__ __noinline__ void direct_row(const Params& p, const WarpArea* wa, const E* ta, const E* tb, float* img,
+                                        int ph) {
+  for (int pw = 0; pw < P; ++pw) {
+    const float gA = (float)ta[pw] * wa->inv_count;
+    const float gB = (float)tb[pw] * wa->inv_count;
+    for (int iy = 0; iy < wa->gh; ++iy) {
+      int ylo, yhi;
+      float ly, hy;
+      const bool vy = axis_tap(sample_coord(wa->start_h, wa->bin_h, ph, iy, wa->gh), p.H, ylo, yhi, ly, hy);
+      for (int ix = 0; ix < wa->gw; ++ix) {
+        int xlo, xhi;
+        float lx, hx;
+        const bool vx = axis_tap(sample_coord(wa->start_w, wa->bin_w, pw, ix, wa->gw), p.W, xlo, xhi, lx, hx);
+        if (vy && vx) {
+          red2(reinterpret_cast<char*>(img + ((size_t)ylo * p.W + xlo) * p.C), pack2(gA * hy * hx, gB * hy * hx));
+          red2(reinterpret_cast<char*>(img + ((size_t)ylo * p.W + xhi) * p.C), pack2(gA * hy * lx, gB * hy * lx));
+          red2(reinterpret_cast<char*>(img + ((size_t)yhi * p.W + xlo) * p.C), pack2(gA * ly * hx, gB * ly * hx));
+          red2(reinterpret_cast<char*>(img + ((size_t)yhi * p.W + xhi) * p.C), pack2(gA * ly * lx, gB * ly * lx));
         }
       }
     }
@@ -296,8 +319,10 @@ __device__ __forceinline__ void sweep(const float4* __restrict__ xt, const f2 (&
 #endif
 }
 
+template <bool BF>
 __global__ void __launch_bounds__(NT, 1)
 roi_align_bwd_cl(const __grid_constant__ CUtensorMap gmap, const Params p) {
+  constexpr int ROWS = Tile<BF>::ROWS, NCH = Tile<BF>::NCH;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WarpArea* wa = reinterpret_cast<WarpArea*>(smem_raw) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -307,7 +332,7 @@ roi_align_bwd_cl(const __grid_constant__ CUtensorMap gmap, const Params p) {
   if (p.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
   else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(policy));
   if (lane == 0) {
-    for (int b = 0; b < NST; ++b) mbar_init(&wa->bar[b], 1);
+    for (int b = 0; b < NBAR; ++b) mbar_init(&wa->bar[b], 1);
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
@@ -330,14 +355,44 @@ roi_align_bwd_cl(const __grid_constant__ CUtensorMap gmap, const Params p) {
   };
   // refill buffer b with the tile NST ahead of tile k of the current item (lane 0 only)
   auto refill = [&](long long cur, long long nxt, int k, int b) {
-    if (k + NST < NCHUNK) issue(cur, k + NST, b);
-    else if (nxt < n_items) issue(nxt, k + NST - NCHUNK, b);
+    if (k + NST < NCH) issue(cur, k + NST, b);
+    else if (nxt < n_items) issue(nxt, k + NST - NCH, b);
+  };
+
+  // bf16 ring (lane 0 only): arrival a of item `it`; after its last use arrival `dead` hands its slot to arrival dead + 4
+  char* const ring = reinterpret_cast<char*>(wa->stage);
+  auto bf_issue = [&](long long it, int a) {
+    const int r = (int)(it / nblk);
+    const int cb = (int)(it - (long long)r * nblk);
+    uint64_t* bar = &wa->bar[a & 3];
+    mbar_expect_tx(bar, BF_BOX_BYTES);
+    tma_tile_load(ring + (a & 3) * BF_BOX_BYTES, &gmap, bar, BF_BOX_ELEMS * bf_box(a), (r * p.C + cb * CB) >> 1, policy);
+  };
+  auto bf_refill = [&](long long cur, long long nxt, int dead) {
+    if (dead + 4 < 8) bf_issue(cur, dead + 4);
+    else if (nxt < n_items) bf_issue(nxt, dead - 4);
+  };
+  auto bf_wait = [&](int s) {  // the arrivals first used by step s
+    if (s == 0) {
+      mbar_wait(&wa->bar[0], 0u);
+      mbar_wait(&wa->bar[1], 0u);
+    } else {
+      mbar_wait(&wa->bar[(s + 1) & 3], (uint32_t)((s + 1) >> 2) & 1u);
+    }
+  };
+  auto bf_release = [&](long long cur, long long nxt, int s) {  // arrivals whose last use was step s
+    bf_refill(cur, nxt, s == 0 ? 1 : (s == 1 ? 0 : s));
+    if (s == 6) bf_refill(cur, nxt, 7);
   };
 
   long long cur = fetch();
   long long nxt = cur < n_items ? fetch() : n_items;
   if (lane == 0 && cur < n_items) {
-    for (int k = 0; k < NST; ++k) issue(cur, k, k);
+    if (BF) {
+      for (int a = 0; a < BF_SLOTS; ++a) bf_issue(cur, a);
+    } else {
+      for (int k = 0; k < NST; ++k) issue(cur, k, k);
+    }
   }
   uint32_t cc = 0;  // tiles consumed by this warp: buffer = cc % NST, mbarrier phase parity = (cc / NST) & 1
   while (cur < n_items) {
@@ -385,18 +440,37 @@ roi_align_bwd_cl(const __grid_constant__ CUtensorMap gmap, const Params p) {
       int iy = 0, ph = 0, b = 0;
       for (int sy = 0; sy <= nsy; ++sy) {  // sample nsy: the zero sentinel that flushes the last row
         if (iy == 0 && ph < P) {
-          const int half = ph % CHUNK_ROWS;
-          if (half == 0) {
-            b = cc % NST;
-            mbar_wait(&wa->bar[b], (cc / NST) & 1u);
-            ++cc;
-          }
-          const float* ta = wa->stage[b] + lane * CHUNK_F + half * P;
+          if (BF) {  // 14 bf16 of channel 2l and of channel 2l+1: 7 + 7 words, widened by shifts
+            const int s = ph >> 1, q = ph & 1;
+            if (q == 0) bf_wait(s);
+            const uint32_t* te = reinterpret_cast<const uint32_t*>(ring + bf_slot_even(s) * BF_BOX_BYTES +
+                                                                   lane * BF_PITCH + (2 * (s & 1) + q) * (2 * P));
+            const uint32_t* to = reinterpret_cast<const uint32_t*>(ring + bf_slot_odd(s) * BF_BOX_BYTES +
+                                                                   lane * BF_PITCH + (2 * ((s + 1) & 1) + q) * (2 * P));
 #pragma unroll
-          for (int j = 0; j < P; ++j) g2[j] = pack2(ta[j], ta[j + 32 * CHUNK_F]);
-          if (half == CHUNK_ROWS - 1 || ph == P - 1) {
-            __syncwarp();  // every lane is done with the tile: refill the buffer NST tiles ahead in the stream
-            if (lane == 0) refill(cur, nxt, ph / CHUNK_ROWS, b);
+            for (int i = 0; i < P / 2; ++i) {
+              const uint32_t e = te[i], o = to[i];
+              g2[2 * i] = ((unsigned long long)(o << 16) << 32) | (unsigned long long)(e << 16);
+              g2[2 * i + 1] = ((unsigned long long)(o & 0xffff0000u) << 32) | (unsigned long long)(e & 0xffff0000u);
+            }
+            if (q == 1) {
+              __syncwarp();  // every lane is done with this step's rows
+              if (lane == 0) bf_release(cur, nxt, s);
+            }
+          } else {
+            const int half = ph % ROWS;
+            if (half == 0) {
+              b = cc % NST;
+              mbar_wait(&wa->bar[b], (cc / NST) & 1u);
+              ++cc;
+            }
+            const float* ta = wa->stage[b] + lane * CHUNK_F + half * P;
+#pragma unroll
+            for (int j = 0; j < P; ++j) g2[j] = pack2(ta[j], ta[j + 32 * CHUNK_F]);
+            if (half == ROWS - 1 || ph == P - 1) {
+              __syncwarp();  // every lane is done with the tile: refill the buffer NST tiles ahead in the stream
+              if (lane == 0) refill(cur, nxt, ph / ROWS, b);
+            }
           }
         }
         const ulonglong2 t = yt[sy];
@@ -422,11 +496,31 @@ roi_align_bwd_cl(const __grid_constant__ CUtensorMap gmap, const Params p) {
     } else {
       // degenerate / foreign RoIs (mode 0) only drain their tiles; mode 2 evaluates every tap directly
 #pragma unroll 1
-      for (int k = 0; k < NCHUNK; ++k) {
+      for (int k = 0; k < NCH; ++k) {
+        if (BF) {
+          bf_wait(k);
+          if (mode == 2) {
+            for (int q = 0; q < 2; ++q) {
+              const __nv_bfloat16* te = reinterpret_cast<const __nv_bfloat16*>(
+                  ring + bf_slot_even(k) * BF_BOX_BYTES + lane * BF_PITCH + (2 * (k & 1) + q) * (2 * P));
+              const __nv_bfloat16* to = reinterpret_cast<const __nv_bfloat16*>(
+                  ring + bf_slot_odd(k) * BF_BOX_BYTES + lane * BF_PITCH + (2 * ((k + 1) & 1) + q) * (2 * P));
+              direct_row<__nv_bfloat16>(p, wa, te, to, img, 2 * k + q);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) bf_release(cur, nxt, k);
+          continue;
+        }
         const int b = cc % NST;
         mbar_wait(&wa->bar[b], (cc / NST) & 1u);
         ++cc;
-        if (mode == 2) direct_chunk(p, wa, wa->stage[b], img, k, lane);
+        if (mode == 2) {
+          for (int half = 0; half < ROWS && ROWS * k + half < P; ++half) {
+            const float* ta = wa->stage[b] + lane * CHUNK_F + half * P;
+            direct_row<float>(p, wa, ta, ta + 32 * CHUNK_F, img, ROWS * k + half);
+          }
+        }
         __syncwarp();
         if (lane == 0) refill(cur, nxt, k, b);
       }
@@ -436,9 +530,11 @@ roi_align_bwd_cl(const __grid_constant__ CUtensorMap gmap, const Params p) {
   }
 }
 
-// scratch [N][HW][C] (channel-permuted within 64-blocks) -> grad_feat [N][C][HW]
+// scratch [N][HW][C] -> grad_feat [N][C][HW].  fp32: channels permuted within 64-blocks (lane l wrote l, l + 32);
+// bf16: natural order (lane l wrote 2l, 2l + 1), rounded to bf16 here (once).
+template <bool BF>
 __global__ void __launch_bounds__(256)
-unpermute_kernel(const float* __restrict__ scratch, float* __restrict__ out, int C, int HW) {
+unpermute_kernel(const float* __restrict__ scratch, void* __restrict__ out, int C, int HW) {
   __shared__ float tile[CB][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int hw0 = blockIdx.x * 32, cb = blockIdx.y, n = blockIdx.z;
@@ -448,16 +544,19 @@ unpermute_kernel(const float* __restrict__ scratch, float* __restrict__ out, int
     const int hw = hw0 + ty + 8 * j;
     if (hw < HW) {
       const float2 v = *reinterpret_cast<const float2*>(src + (size_t)hw * C + 2 * tx);
-      tile[tx][ty + 8 * j] = v.x;
-      tile[tx + 32][ty + 8 * j] = v.y;
+      tile[BF ? 2 * tx : tx][ty + 8 * j] = v.x;
+      tile[BF ? 2 * tx + 1 : tx + 32][ty + 8 * j] = v.y;
     }
   }
   __syncthreads();
-  float* dst = out + ((size_t)n * C + cb * CB) * HW;
+  const size_t base = ((size_t)n * C + cb * CB) * HW;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = ty + 8 * j;
-    if (hw0 + tx < HW) dst[(size_t)c * HW + hw0 + tx] = tile[c][tx];
+    if (hw0 + tx < HW) {
+      if (BF) reinterpret_cast<__nv_bfloat16*>(out)[base + (size_t)c * HW + hw0 + tx] = __float2bfloat16_rn(tile[c][tx]);
+      else reinterpret_cast<float*>(out)[base + (size_t)c * HW + hw0 + tx] = tile[c][tx];
+    }
   }
 }
 
@@ -484,19 +583,22 @@ static EncodeTiledFn encode_fn() {
 }  // namespace cl
 
 bool bwd_cl_fits(int C, int H, int W, int R, int dtype, const void* gout) {
-  return dtype == UNIT_F32 && (C % cl::CB) == 0 && H >= 2 && W >= 2 && ((uintptr_t)gout & 15) == 0 &&
+  return (dtype == UNIT_F32 || dtype == UNIT_BF16) && (C % cl::CB) == 0 && H >= 2 && W >= 2 &&
+         ((uintptr_t)gout & 15) == 0 &&
          (long long)R * C < (1ll << 31) && cl::encode_fn() != nullptr;
 }
 
 // workspace: [256 B counter][N*H*W*C fp32 channel-last image]
 int launch_bwd_cl(const void* gout, const float* rois, void* gfeat, void* ws, int N, int C, int H, int W, int R,
-                  float scale, int sr, int aligned, cudaStream_t st) {
+                  float scale, int sr, int aligned, int dtype, cudaStream_t st) {
   using namespace cl;
+  const bool bf = dtype == UNIT_BF16;
   CUtensorMap map;
   {
-    cuuint64_t dims[2] = {(cuuint64_t)(P * P), (cuuint64_t)R * C};
+    // fp32: rows = channels (196 floats, 784 B).  bf16: rows = channel PAIRS (2 x 196 bf16, 784 B).
+    cuuint64_t dims[2] = {(cuuint64_t)(bf ? 2 * P * P : P * P), (cuuint64_t)R * C / (bf ? 2 : 1)};
     cuuint64_t strides[1] = {(cuuint64_t)(P * P) * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)CHUNK_F, (cuuint32_t)CB};
+    cuuint32_t box[2] = {(cuuint32_t)(bf ? BF_BOX_ELEMS : CHUNK_F), (cuuint32_t)(bf ? CB / 2 : CB)};
     cuuint32_t estr[2] = {1, 1};
     const char* ep = getenv("UNIT_ROI_BWD_PROMO");
     const int promo = ep ? atoi(ep) : 2;
@@ -504,7 +606,8 @@ int launch_bwd_cl(const void* gout, const float* rois, void* gfeat, void* ws, in
                                      : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                      : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
                                                   : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-    CUresult rc = encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(gout), dims, strides, box,
+    CUresult rc = encode_fn()(&map, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                              const_cast<void*>(gout), dims, strides, box,
                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, pr,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     UNIT_REQUIRE(rc == CUDA_SUCCESS, "roi_align_bwd: cuTensorMapEncodeTiled failed (%d)", (int)rc);
@@ -533,15 +636,22 @@ int launch_bwd_cl(const void* gout, const float* rois, void* gfeat, void* ws, in
   zero4_kernel<<<zgrid, 256, 0, st>>>((float4*)ws, n4);
   UNIT_CHECK_LAUNCH("zero4_kernel");
   const size_t smem = (size_t)NW * sizeof(WarpArea);
-  UNIT_CUDA(cudaFuncSetAttribute(roi_align_bwd_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long items = (long long)R * (C / CB);
   long long grid = (items + NW - 1) / NW;
   if (grid > sm_count()) grid = sm_count();
   if (grid < 1) grid = 1;
-  roi_align_bwd_cl<<<(int)grid, NT, smem, st>>>(map, p);
-  UNIT_CHECK_LAUNCH("roi_align_bwd_cl");
   dim3 tgrid((H * W + 31) / 32, C / CB, N);
-  unpermute_kernel<<<tgrid, 256, 0, st>>>(p.scratch, (float*)gfeat, C, H * W);
+  if (bf) {
+    UNIT_CUDA(cudaFuncSetAttribute(roi_align_bwd_cl<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roi_align_bwd_cl<true><<<(int)grid, NT, smem, st>>>(map, p);
+    UNIT_CHECK_LAUNCH("roi_align_bwd_cl");
+    unpermute_kernel<true><<<tgrid, 256, 0, st>>>(p.scratch, gfeat, C, H * W);
+  } else {
+    UNIT_CUDA(cudaFuncSetAttribute(roi_align_bwd_cl<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roi_align_bwd_cl<false><<<(int)grid, NT, smem, st>>>(map, p);
+    UNIT_CHECK_LAUNCH("roi_align_bwd_cl");
+    unpermute_kernel<false><<<tgrid, 256, 0, st>>>(p.scratch, gfeat, C, H * W);
+  }
   UNIT_CHECK_LAUNCH("unpermute_kernel");
   return UNIT_OK;
 }
