@@ -159,7 +159,8 @@ int unit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, in
   if (R == 0) return UNIT_OK;
   UNIT_REQUIRE(feat && rois && out, "roi_align_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (rois_sorted && PH == 14 && PW == 14 && N > 0 && fwd_band_fits(C, H, W, dtype) && dtype == UNIT_F32 &&
+  if (rois_sorted && PH == 14 && PW == 14 && N > 0 && fwd_band_fits(C, H, W, dtype) &&
+      (dtype == UNIT_F32 || getenv("UNIT_ROI_FWD_BAND_BF16")) &&
       !getenv("UNIT_ROI_FWD_V3")) {  // bf16 I/O: the pair-interleaved kernel below loads its slab faster
     const size_t need = offsets_bytes(N) + fwd_band_workspace_bytes(R);
     if (!workspace || workspace_bytes < need) {
