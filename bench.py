@@ -539,6 +539,68 @@ def run_ours(args):
                 "ms_per_call": time_kernel(dec_nms, 10, flush), "candidates": n_cand,
                 "what": "softmax_decode + detect (parallel filter, grouped NMS, top-100) for 2 images x 1000 proposals "
                         "x 80 classes, CUDA events, L2 flushed"}
+            # BASELINE.json configs[2] size: Matcher + fg/bg sampling, 64 images x (1000 proposals + GT) in one call
+            from unit_b200 import layers as _layers
+            lp, lt = [], []
+            for _ in range(64):
+                gtb = _boxes(4, IMG_HW[0], IMG_HW[1], g, 32.0)
+                pb64 = torch.cat([_boxes(1000, IMG_HW[0], IMG_HW[1], g), gtb])
+                lp.append(wl.Instances(IMG_HW, proposal_boxes=wl.Boxes(pb64.to(device)),
+                                       objectness_logits=torch.zeros(len(pb64), device=device)))
+                lt.append(wl.Instances(IMG_HW, gt_boxes=wl.Boxes(gtb.to(device)),
+                                       gt_classes=torch.randint(0, 20, (4,), generator=g).to(device)))
+            gen64 = _seeded(64)
+            ms64 = wall_ms(lambda: _layers.label_and_sample(lp, lt, num_classes=20, batch_size_per_image=512,
+                                                            positive_fraction=0.25, thresholds=[0.5], labels=[0, 1],
+                                                            generator=gen64))
+            aux["label_sample_batch64"] = {
+                "ms_per_call": ms64, "images_per_s": 64 / (ms64 * 1e-3),
+                "what": "layers.label_and_sample, 64 images x 1004 proposals: fused IoU+match, label, host randperm "
+                        "draw, gather (wall clock incl. the one D2H of the fg/bg counts and building 64 Instances)"}
+            # BASELINE.json configs[4] size: transferred mask logits -> class select + sigmoid -> paste, 100 detections
+            D, KM = 100, 80
+            mspec = ops.TransferSpec(KM, list(range(60)), list(range(60, 80)), device)
+            mlog = torch.randn(D, KM, 28, 28, generator=g).to(device)
+            msim = torch.softmax(torch.randn(D, 20, 60, generator=g), -1).to(device)
+            mcls = torch.randint(0, KM, (D,), generator=g).to(device)
+            mbox = _boxes(D, IMG_HW[0], IMG_HW[1], g, 24.0).to(device)
+
+            def mask_path():
+                _, probs = ops.mask_transfer(mlog, msim, mspec, None, mcls)
+                return ops.mask_paste(probs[:, 0], mbox, IMG_HW, 0.5)
+
+            for _ in range(3):
+                mask_path()
+            aux["coco_mask_transfer_paste"] = {
+                "ms_per_call": time_kernel(mask_path, 10, flush),
+                "what": "mask_transfer (per-RoI similarity, 60 base -> 20 novel, class select + sigmoid) + mask_paste "
+                        "of 100 detections into 800x1333, CUDA events, L2 flushed"}
+            # weak-image branch of base training: MIL loss + 3 OICR refinements (targets + weighted CE), fwd + grads
+            Rw, Kw = 2 * 2000, 20
+            wc, wd_ = torch.randn(Rw, Kw, generator=g).to(device), torch.randn(Rw, Kw, generator=g).to(device)
+            wo = [torch.randn(Rw, Kw + 1, generator=g).to(device) for _ in range(3)]
+            wb = torch.cat([_boxes(2000, IMG_HW[0], IMG_HW[1], g) for _ in range(2)]).to(device)
+            woff = ops.offsets_from_counts([2000, 2000], device)
+            wgt = torch.zeros(2, Kw)
+            wgt[0, [2, 7, 11]] = 1
+            wgt[1, [5]] = 1
+            wgt = wgt.to(device)
+
+            def weak_path():
+                loss, probs, _ = ops.mil_loss(wc, wd_, woff, wgt, 1.0)
+                for i in range(3):
+                    if i:
+                        probs, _ = ops.softmax_decode(wo[i - 1], None, None, want_boxes=False)
+                    lab, wgh, _, _ = ops.oicr_targets(probs, wb, woff, wgt, [0.5], [0, 1], 0.1)
+                    loss = loss + ops.weighted_ce_loss(wo[i], lab, wgh)
+                return loss
+
+            for _ in range(3):
+                weak_path()
+            aux["weak_losses"] = {
+                "ms_per_call": time_kernel(weak_path, 10, flush),
+                "what": "MIL image loss + 3 x (OICR pseudo-labelling + weighted CE) with gradients, 2 images x 2000 "
+                        "proposals, K=20: 13 launches, eager, CUDA events"}
             wl.head.train()
 
     # CPU baseline on the box's host cores (rank 0, N = 1 only): the oracle port on a bounded sample

@@ -1,0 +1,41 @@
+"""Micro-benchmark: mask transfer and mask paste at the COCO size (100 detections, 80 classes, 28x28 -> 800x1333)."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import torch
+from unit_b200 import ops
+from conftest import random_boxes, seeded
+
+
+def ev(fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(n):
+        fn()
+    e.record(); torch.cuda.synchronize()
+    return s.elapsed_time(e) / n
+
+
+def main():
+    g = seeded(3)
+    dev = torch.device('cuda')
+    D, K = 100, 80
+    spec = ops.TransferSpec(K, list(range(60)), list(range(60, 80)), dev)
+    logits = torch.randn(D, K, 28, 28, generator=g).cuda()
+    sim = torch.softmax(torch.randn(D, 20, 60, generator=g), -1).cuda()
+    cls = torch.randint(0, K, (D,), generator=g).cuda()
+    boxes = random_boxes(D, 800, 1333, g, 24.0).cuda()
+    _, probs = ops.mask_transfer(logits, sim, spec, None, cls)
+    m = probs[:, 0].contiguous()
+    out = {"mask_transfer_ms": ev(lambda: ops.mask_transfer(logits, sim, spec, None, cls)),
+           "mask_paste_ms": ev(lambda: ops.mask_paste(m, boxes, (800, 1333), 0.5)),
+           "paste_bytes_written": D * 800 * 1333}
+    out["mask_paste_GBs"] = out["paste_bytes_written"] / out["mask_paste_ms"] / 1e6
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()

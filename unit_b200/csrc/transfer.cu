@@ -13,6 +13,8 @@
 // cuBLAS); this file is the memory-bound part and never leaves fp32.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace unit {
@@ -310,18 +312,64 @@ __device__ __forceinline__ float paste_sample(const float* __restrict__ mk, int 
   return __fadd_rn(__fadd_rn(__fadd_rn(nw, ne), sw), se);
 }
 
+// PX pixels per thread, one PX-byte store.  4 (not 16): a warp then spans 128 pixels of a row, so far fewer warps
+// straddle a box window and drag all their lanes through the sampling path.
+#ifndef UNIT_PASTE_PX
+#define UNIT_PASTE_PX 4
+#endif
+constexpr int PX = UNIT_PASTE_PX;
+static_assert(PX == 4 || PX == 16, "mask_paste: 4 or 16 pixels per thread");
+__device__ __forceinline__ void paste_store(uint8_t* dst, const unsigned char* v) {
+  if (PX == 16) {
+    uint4 q;
+    memcpy(&q, v, 16);
+    *reinterpret_cast<uint4*>(dst) = q;
+  } else {
+    uint32_t q;
+    memcpy(&q, v, 4);
+    *reinterpret_cast<uint32_t*>(dst) = q;
+  }
+}
 __global__ void mask_paste_kernel(const float* __restrict__ masks, const float4* __restrict__ boxes, int D, int M,
                                   int H, int W, float thr, uint8_t* __restrict__ out) {
   const long long total = (long long)D * H * W;
-  const long long start = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  const long long start = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PX;
   if (start >= total) return;
   const long long hw = (long long)H * W;
-  int d = (int)(start / hw);
-  long long rem = start - (long long)d * hw;
-  int y = (int)(rem / W), x = (int)(rem - (long long)y * W);
-  unsigned char v[16];
+  int d, y, x;
+  if (total < (1ll << 31)) {  // 32-bit index arithmetic (64-bit divisions cost more than the rest of the thread)
+    const unsigned s32 = (unsigned)start, hw32 = (unsigned)hw;
+    d = (int)(s32 / hw32);
+    const unsigned rem = s32 - (unsigned)d * hw32;
+    y = (int)(rem / (unsigned)W);
+    x = (int)(rem - (unsigned)y * (unsigned)W);
+  } else {
+    d = (int)(start / hw);
+    const long long rem = start - (long long)d * hw;
+    y = (int)(rem / W);
+    x = (int)(rem - (long long)y * W);
+  }
+  unsigned char v[PX];
   float4 bx = __ldg(boxes + d);
-  for (int i = 0; i < 16; ++i) {
+  {
+    // Fast reject of a whole PX-pixel run (most of the image lies outside the box): a pixel can only be sampled when
+    // its centre is within bw / M resp. bh / M of the box; one extra pixel of margin covers every rounding of the
+    // exact expressions below, which still decide every pixel that is not rejected here.
+    const float bw = bx.z - bx.x, bh = bx.w - bx.y;
+    if (x + PX - 1 < W && start + PX <= total && bw > 0.f && bh > 0.f && bw < 1e6f && bh < 1e6f &&
+        fabsf(bx.x) < 1e6f && fabsf(bx.y) < 1e6f && ((((uintptr_t)out) + start) & (PX - 1)) == 0) {
+      const float mx = bw / (float)M + 1.f, my = bh / (float)M + 1.f;
+      const float py = (float)y + 0.5f;
+      if (py < bx.y - my || py > bx.w + my || (float)(x + PX - 1) + 0.5f < bx.x - mx || (float)x + 0.5f > bx.z + mx) {
+        const unsigned char zb = (0.f >= thr) ? 1 : 0;
+#pragma unroll
+        for (int i = 0; i < PX; ++i) v[i] = zb;
+        paste_store(out + start, v);
+        return;
+      }
+    }
+  }
+  for (int i = 0; i < PX; ++i) {
     unsigned char o = 0;
     if (start + i < total) {
       const float bw = __fsub_rn(bx.z, bx.x), bh = __fsub_rn(bx.w, bx.y);
@@ -350,12 +398,52 @@ __global__ void mask_paste_kernel(const float* __restrict__ masks, const float4*
     }
     v[i] = o;
   }
-  if (start + 16 <= total && ((((uintptr_t)out) + start) & 15) == 0) {
-    uint4 q;
-    memcpy(&q, v, 16);
-    *reinterpret_cast<uint4*>(out + start) = q;
+  if (start + PX <= total && ((((uintptr_t)out) + start) & (PX - 1)) == 0) {
+    paste_store(out + start, v);
   } else {
-    for (int i = 0; i < 16 && start + i < total; ++i) out[start + i] = v[i];
+    for (int i = 0; i < PX && start + i < total; ++i) out[start + i] = v[i];
+  }
+}
+
+// One pixel, the exact expression chain shared by both paste kernels.
+__device__ __forceinline__ unsigned char paste_pixel(const float* __restrict__ mk, int M, float4 bx, int x, int y,
+                                                     float thr) {
+  const float bw = __fsub_rn(bx.z, bx.x), bh = __fsub_rn(bx.w, bx.y);
+  const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+  const float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(px, bx.x), bw), 2.f), 1.f);
+  const float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(py, bx.y), bh), 2.f), 1.f);
+  const float lim = 1.f + 2.f / (float)M;
+  if ((fabsf(gx) < lim && fabsf(gy) < lim) || !(gx == gx) || !(gy == gy)) return paste_sample(mk, M, gx, gy) >= thr ? 1 : 0;
+  return 0.f >= thr ? 1 : 0;
+}
+
+// Box-centric paste for thr > 0 (pixels outside the window are 0): the canvas is cleared by a memset and one CTA per
+// (detection, strip of WIN_ROWS rows) visits only the pixels of its strip that lie in the box window; strips outside
+// the window exit at once.  Irregular boxes (empty, non-finite, huge) get the whole canvas as their window.
+constexpr int WIN_ROWS = 8;
+__global__ void __launch_bounds__(256) mask_paste_window_kernel(const float* __restrict__ masks,
+                                                                const float4* __restrict__ boxes, int M, int H, int W,
+                                                                float thr, uint8_t* __restrict__ out) {
+  const int d = blockIdx.y;
+  const float4 bx = __ldg(boxes + d);
+  const float bw = bx.z - bx.x, bh = bx.w - bx.y;
+  int x_lo = 0, x_hi = W - 1, y_lo = 0, y_hi = H - 1;
+  if (bw > 0.f && bh > 0.f && bw < 1e6f && bh < 1e6f && fabsf(bx.x) < 1e6f && fabsf(bx.y) < 1e6f) {
+    // a pixel is sampled only when its centre is within bw / M (bh / M) of the box; + 1 pixel covers all rounding
+    const float mx = bw / (float)M + 1.f, my = bh / (float)M + 1.f;
+    x_lo = max(0, (int)floorf(bx.x - mx - 0.5f));
+    x_hi = min(W - 1, (int)ceilf(bx.z + mx - 0.5f));
+    y_lo = max(0, (int)floorf(bx.y - my - 0.5f));
+    y_hi = min(H - 1, (int)ceilf(bx.w + my - 0.5f));
+  }
+  const int r0 = max(y_lo, (int)blockIdx.x * WIN_ROWS), r1 = min(y_hi, (int)blockIdx.x * WIN_ROWS + WIN_ROWS - 1);
+  if (r0 > r1 || x_lo > x_hi) return;
+  const float* mk = masks + (long long)d * M * M;
+  uint8_t* dst = out + (long long)d * H * W;
+  const int ww = x_hi - x_lo + 1, n = (r1 - r0 + 1) * ww;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int y = r0 + i / ww, x = x_lo + i % ww;
+    dst[(long long)y * W + x] = paste_pixel(mk, M, bx, x, y, thr);
   }
 }
 
@@ -460,7 +548,15 @@ int unit_mask_paste(const float* masks, const float* boxes, int D, int M, int im
   UNIT_REQUIRE(masks && boxes && out, "mask_paste: null pointer");
   UNIT_REQUIRE((((uintptr_t)boxes) & 15) == 0, "mask_paste: boxes must be 16-byte aligned");
   const long long total = (long long)D * img_h * img_w;
-  const long long threads = (total + 15) / 16;
+  if (threshold > 0.f && D <= 65535 && !getenv("UNIT_PASTE_FLAT")) {  // outside value is 0: clear, then visit the box windows only
+    UNIT_CUDA(cudaMemsetAsync(out, 0, (size_t)total, (cudaStream_t)stream));
+    dim3 grid(cdiv(img_h, unit::transfer::WIN_ROWS), D);
+    mask_paste_window_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(masks, (const float4*)boxes, M, img_h, img_w,
+                                                                     threshold, out);
+    UNIT_CHECK_LAUNCH("mask_paste_window_kernel");
+    return UNIT_OK;
+  }
+  const long long threads = (total + unit::transfer::PX - 1) / unit::transfer::PX;
   mask_paste_kernel<<<cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(masks, (const float4*)boxes, D, M, img_h,
                                                                          img_w, threshold, out);
   UNIT_CHECK_LAUNCH("mask_paste_kernel");
