@@ -105,6 +105,30 @@ def test_containers():
     assert Boxes(torch.empty(0)).tensor.shape == (0, 4)
 
 
+def test_cat_returns_a_view_only_for_adjacent_row_blocks():
+    """layers.cat: per-image slices of one flat buffer (what the sampling kernel hands out) come back as ONE view --
+    no copy kernel in the step graph; anything else is an ordinary torch.cat."""
+    from unit_b200.layers import cat
+
+    flat = torch.arange(40, dtype=torch.float32).reshape(10, 4)
+    parts = [flat[0:3], flat[3:3], flat[3:7], flat[7:10]]
+    v = cat(parts)
+    assert torch.equal(v, flat) and v.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr()
+    assert cat([flat[2:5], flat[5:9]]).storage_offset() == 8                      # starts inside the buffer
+    for other in ([flat[0:3], flat[4:7]],                                           # gap
+                  [flat[3:7], flat[0:3]],                                           # out of order
+                  [flat[0:3], flat[3:7].clone()],                                   # another buffer
+                  [flat[0:3, :2], flat[3:7, :2]],                                   # not contiguous
+                  [flat[0:3], flat[3:7].double()]):                                 # (dtype promotion -> torch.cat)
+        out = cat(list(other))
+        assert out.untyped_storage().data_ptr() != flat.untyped_storage().data_ptr()
+        assert torch.equal(out, torch.cat(list(other)))
+    w = torch.zeros(6, 2, requires_grad=True)
+    g = cat([w[0:2], w[2:6]])
+    assert g.grad_fn is not None and g.grad_fn.name().startswith("Cat")            # autograd keeps the real cat
+    assert cat([flat[0:3]]) is not None and cat([flat[1:2]]).shape == (1, 4)
+
+
 def test_no_cpu_fallback():
     from unit_b200 import ops
 
