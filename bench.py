@@ -255,6 +255,25 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs NVML reports as closest to its GPU, BEFORE any pinned host buffer is allocated: with
+    one rank per GPU the 34.5 MB/step host->device copies then come from the GPU's own NUMA node (what a launcher
+    with --cpu-bind does).  Returns the CPU count bound to, or None when NVML cannot tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:  # CUDA_VISIBLE_DEVICES may renumber the devices: go through the PCI address
+            pr = torch.cuda.get_device_properties(index)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(
+                "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -407,6 +426,8 @@ def run_ours(args):
                          "CPU baseline")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    affinity = bind_to_gpu_numa_node(local_rank) if not args.no_affinity else None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -606,6 +627,7 @@ def run_ours(args):
     # CPU baseline on the box's host cores (rank 0, N = 1 only): the oracle port on a bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core again
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         w, meta, x, xw, gp = cpu_workload()
@@ -641,7 +663,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "gpu_launches_note": "kernels of libunit_b200.so executed in the timed region, directly or as nodes of "
                                  "the replayed CUDA graphs (cuBLAS GEMMs and ATen kernels not counted)",
-            "cuda_graphs": bool(wl.use_graph), "label_prefetch": bool(wl.prefetch),
+            "cuda_graphs": bool(wl.use_graph), "label_prefetch": bool(wl.prefetch), "cpu_affinity": affinity,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "aux": aux,
         }
         print(json.dumps(line), flush=True)
@@ -658,6 +680,7 @@ def main():
     ap.add_argument("--dtype", choices=["f32", "bf16"], default="f32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to its GPU's NUMA-local CPUs")
     ap.add_argument("--no-prefetch", action="store_true",
                     help="do not start the labelling (graph A) of step i+1 while step i runs")
     ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary inference-side measurements")
