@@ -123,8 +123,8 @@ class RoIStage:
         if self.bucket is not None:
             self.bucket.zero_()
         boxes = [p.proposal_boxes for p in sampled]
-        rois = layers.cat([torch.cat((b.tensor.new_full((len(b), 1), float(i)), b.tensor), dim=1)
-                           for i, b in enumerate(boxes)])
+        rois = ops.boxes_to_rois(layers.cat([b.tensor for b in boxes]),
+                                 ops.offsets_from_counts([len(b) for b in boxes], features.device))
         pool = head.box_pooler
         pooled = ops.roi_align_forward(features, rois, pool.output_size, pool.scales[0], pool.sampling_ratio,
                                        pool.aligned, True)
