@@ -216,17 +216,21 @@ def draw_permutations(counts_h: Sequence[Sequence[int]], batch_size_per_image: i
         nso.append(nso[-1] + num_neg)
     d = SampleDraw()
     d.pso, d.nso, d.n_img = pso, nso, n_img
-    offs = torch.tensor(ppo + pno + pso + nso, dtype=torch.int64)
+    # the four int32 offset arrays travel in the tail of the int64 buffer, stored AS int32 (the device side views the
+    # tail as int32: no conversion kernel in the step)
+    offs = torch.tensor(ppo + pno + pso + nso, dtype=torch.int32)
     if capacity is None:
         d.pos_len, d.neg_len = ppo[-1], pno[-1]
-        d.host = torch.cat(perm_pos + perm_neg + [offs])
+        tail = torch.zeros(offs.numel(), dtype=torch.int64)
+        tail.view(torch.int32)[:offs.numel()] = offs
+        d.host = torch.cat(perm_pos + perm_neg + [tail])
     else:
         assert ppo[-1] <= capacity and pno[-1] <= capacity
         d.pos_len = d.neg_len = capacity
         d.host = out if out is not None else torch.empty(2 * capacity + offs.numel(), dtype=torch.int64)
         torch.cat(perm_pos, out=d.host[:ppo[-1]])
         torch.cat(perm_neg, out=d.host[capacity:capacity + pno[-1]])
-        d.host[2 * capacity:] = offs
+        d.host[2 * capacity:].view(torch.int32)[:offs.numel()] = offs
     return d
 
 
@@ -238,7 +242,7 @@ def sample_from_draw(lm: LabelMatch, draw: SampleDraw, devbuf: torch.Tensor, pro
     S = pso[-1] + nso[-1]
     d_perm_pos = devbuf[:draw.pos_len]
     d_perm_neg = devbuf[draw.pos_len:draw.pos_len + draw.neg_len]
-    offs = devbuf[draw.pos_len + draw.neg_len:].to(torch.int32)
+    offs = devbuf[draw.pos_len + draw.neg_len:].view(torch.int32)
     k = n_img + 1
     sampled, s_boxes, s_classes, s_matched, s_gt = ops.sample_gather(
         lm.pos_idx, lm.neg_idx, d_perm_pos, offs[:k], d_perm_neg, offs[k:2 * k], offs[2 * k:3 * k], offs[3 * k:4 * k],
