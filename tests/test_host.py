@@ -129,6 +129,33 @@ def test_cat_returns_a_view_only_for_adjacent_row_blocks():
     assert cat([flat[0:3]]) is not None and cat([flat[1:2]]).shape == (1, 4)
 
 
+def test_draw_permutations_layout_and_generator_order():
+    """layers.draw_permutations = the host half of [D2] subsample_labels: randperm(#pos) then randperm(#neg), image by
+    image, from ONE generator; the int32 offset arrays ride in the tail of the int64 buffer (viewed as int32)."""
+    from unit_b200.layers import draw_permutations
+
+    counts = [(40, 900), (0, 1000), (300, 5)]
+    gen = torch.Generator().manual_seed(9)
+    d = draw_permutations(counts, 512, 0.25, gen)
+    ref = torch.Generator().manual_seed(9)
+    want = [torch.randperm(n, generator=ref) for pair in counts for n in pair]
+    pos = torch.cat(want[0::2]); neg = torch.cat(want[1::2])
+    assert d.pos_len == 340 and d.neg_len == 1905
+    assert torch.equal(d.host[:340], pos) and torch.equal(d.host[340:340 + 1905], neg)
+    offs = d.host[340 + 1905:].view(torch.int32)
+    k = len(counts) + 1
+    assert offs[:k].tolist() == [0, 40, 40, 340]                      # full positive permutation lengths
+    assert offs[k:2 * k].tolist() == [0, 900, 1900, 1905]             # full negative permutation lengths
+    assert offs[2 * k:3 * k].tolist() == [0, 40, 40, 168] == d.pso    # taken positives: min(#pos, 128)
+    assert offs[3 * k:4 * k].tolist() == [0, 472, 984, 989] == d.nso  # taken negatives: min(#neg, 512 - pos)
+    # fixed-capacity form (CUDA-graph replay): same draws into a caller-owned buffer
+    buf = torch.full((2 * 2048 + 4 * k,), -1, dtype=torch.int64)
+    d2 = draw_permutations(counts, 512, 0.25, torch.Generator().manual_seed(9), capacity=2048, out=buf)
+    assert d2.host is buf and d2.pos_len == d2.neg_len == 2048
+    assert torch.equal(buf[:340], pos) and torch.equal(buf[2048:2048 + 1905], neg)
+    assert buf[4096:].view(torch.int32)[:4 * k].tolist() == offs[:4 * k].tolist()
+
+
 def test_no_cpu_fallback():
     from unit_b200 import ops
 
