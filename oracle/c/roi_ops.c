@@ -144,3 +144,49 @@ void oracle_roi_align_fwd(const float* feat, int N, int C, int H, int W, const f
     }
   }
 }
+
+/* weak_detector_fast_rcnn.py:353-396 for ONE image: get_proposal_clusters (for each class of `classes` -- sorted,
+ * unique -- the proposal with the largest probs[r][c] among rows not picked yet, first row on ties; a picked row
+ * counts as all-zero afterwards), then pairwise_iou(picked boxes, proposals) + Matcher + the label / loss-weight
+ * rules of label_and_sample_proposals and compute_loss_inputs.  probs [R][ld]; out: labels [R], weights [R],
+ * picked [G] (row index per class). */
+void oracle_oicr_targets(const float* probs, int ld, const float* boxes, int R, const int64_t* classes, int G,
+                         const float* thr, const int* match_labels, int T, float bg_threshold, int num_classes,
+                         int64_t* labels, float* weights, int64_t* picked) {
+  if (R == 0) return;
+  unsigned char* used = (unsigned char*)calloc((size_t)R, 1);
+  float* score = (float*)malloc(sizeof(float) * (size_t)(G > 0 ? G : 1));
+  float* gbox = (float*)malloc(sizeof(float) * 4 * (size_t)(G > 0 ? G : 1));
+  for (int g = 0; g < G; ++g) {
+    const int c = (int)classes[g];
+    float best = used[0] ? 0.f : probs[c];
+    int arg = 0;
+    for (int r = 1; r < R; ++r) {
+      const float v = used[r] ? 0.f : probs[(size_t)r * ld + c];
+      if (v > best) {
+        best = v;
+        arg = r;
+      }
+    }
+    used[arg] = 1;
+    picked[g] = arg;
+    score[g] = best;
+    memcpy(gbox + 4 * g, boxes + 4 * arg, 4 * sizeof(float));
+  }
+  float* iou = (float*)malloc(sizeof(float) * (size_t)(G > 0 ? G : 1) * (size_t)R);
+  int64_t* m = (int64_t*)malloc(sizeof(int64_t) * (size_t)R);
+  int8_t* l = (int8_t*)malloc((size_t)R);
+  float* v = (float*)malloc(sizeof(float) * (size_t)R);
+  oracle_pairwise_iou(gbox, G, boxes, R, iou);
+  oracle_matcher(iou, G, R, thr, match_labels, T, m, l, v);
+  for (int r = 0; r < R; ++r) {
+    if (G == 0) {
+      labels[r] = num_classes;
+      weights[r] = 0.f;
+      continue;
+    }
+    labels[r] = l[r] == 1 ? classes[m[r]] : (l[r] == 0 ? num_classes : -1);
+    weights[r] = (bg_threshold > 0.f && v[r] < bg_threshold) ? 0.f : score[m[r]];
+  }
+  free(used); free(score); free(gbox); free(iou); free(m); free(l); free(v);
+}

@@ -67,3 +67,49 @@ def test_c_roi_align_matches_torchvision(clib):
                               _p(out))
     ref = torch.ops.torchvision.roi_align(feat, rois, 1 / 16, 14, 14, 0, True)
     assert_close_rms(torch.from_numpy(out), ref, 1e-5, "C roi_align")
+
+
+def test_c_oicr_targets_match_reference_fixture(clib):
+    """OICR pseudo-labelling in plain C vs the reference run verbatim (tests/golden/weak_losses.pt) and vs the torch
+    restatement on a larger seeded case with ties: labels and picked proposals bit-exact, weights exact copies."""
+    from conftest import load_golden
+    from oracle import unit_ref
+
+    def run_c(probs, boxes, classes, bg, K):
+        probs = np.ascontiguousarray(probs.numpy(), np.float32)
+        labels, weights, picked = [], [], []
+        start = 0
+        for b, cls in zip(boxes, classes):
+            R = len(b)
+            uniq = np.ascontiguousarray(torch.unique(cls).numpy(), np.int64)
+            lab, w, pk = np.zeros(R, np.int64), np.zeros(R, np.float32), np.zeros(len(uniq), np.int64)
+            thr, ml = np.array([0.5], np.float32), np.array([0, 1], np.int32)
+            p = np.ascontiguousarray(probs[start:start + R])
+            clib.oracle_oicr_targets(_p(p), p.shape[1], _p(np.ascontiguousarray(b.numpy(), np.float32)), R, _p(uniq),
+                                     len(uniq), _p(thr), _p(ml), 1, ctypes.c_float(bg), K, _p(lab), _p(w), _p(pk))
+            start += R
+            labels.append(torch.from_numpy(lab)); weights.append(torch.from_numpy(w)); picked.append(torch.from_numpy(pk))
+        return torch.cat(labels), torch.cat(weights), picked
+
+    gold = load_golden("weak_losses.pt")
+    probs = gold["mil_scores"]
+    for idx, sup in enumerate(gold["supervision"]):
+        if idx > 0:
+            probs = torch.softmax(gold["oicr_scores"][idx - 1], -1)
+        lab, w, _ = run_c(probs, gold["proposal_boxes"], gold["targets"], gold["bg_threshold"], 20)
+        assert torch.equal(lab, sup["labels"]) and torch.equal(w, sup["cls_weights"])
+    g = seeded(41)
+    boxes = []
+    for n in (700, 33, 1200):
+        b = random_boxes(n, 600, 800, g, 16.0)
+        b[:n // 2] = b[torch.randint(0, 8, (n // 2,), generator=g)] + torch.randn(n // 2, 4, generator=g) * 6
+        b[:, 2:] = torch.maximum(b[:, 2:], b[:, :2] + 2)
+        boxes.append(b)
+    classes = [torch.tensor([7, 3, 7, 60]), torch.tensor([0]), torch.tensor([79, 5, 12, 12, 41])]
+    probs = torch.softmax(torch.randn(1933, 81, generator=g) * 3, -1)
+    dup = torch.arange(0, 1932, 5)
+    probs[dup + 1] = probs[dup]
+    want_l, want_w, want_p = unit_ref.oicr_targets(probs, boxes, classes, [0.5], [0, 1], 0.1, 80)
+    lab, w, pk = run_c(probs, boxes, classes, 0.1, 80)
+    assert torch.equal(lab, want_l) and torch.equal(w, want_w)
+    assert all(torch.equal(a, b) for a, b in zip(pk, want_p))
