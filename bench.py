@@ -608,7 +608,7 @@ def run_ours(args):
             wgt = wgt.to(device)
 
             def weak_path():
-                loss, probs, _ = ops.mil_loss(wc, wd_, woff, wgt, 1.0)
+                loss, probs, _ = ops.mil_loss(wc, wd_, woff, wgt, 1.0, max_rows=2000)
                 for i in range(3):
                     if i:
                         probs, _ = ops.softmax_decode(wo[i - 1], None, None, want_boxes=False)

@@ -226,7 +226,9 @@ int unit_mask_paste(const float* masks, const float* boxes, int D, int M, int im
  *   proposals of the image); class_vector[i] = sum_r x; loss = multiplier * mean BCE(clamp(class_vector, 1e-6,
  *   1 - 1e-6), gt_vector).  cls_logits / det_logits [R,K] (already divided by their temperatures), gt_vector [n_img,K]
  *   in {0,1}.  Writes mil_scores [R,K] (= x, the first OICR supervision), class_vector [n_img,K], loss [1] and the
- *   gradients d_cls, d_det [R,K] of loss (for upstream gradient 1).  workspace: n_img floats.
+ *   gradients d_cls, d_det [R,K] of loss (for upstream gradient 1).  max_rows = the largest per-image row count (a host
+ *   hint that sizes the grid: one CTA per 128 rows of an image; R is always a valid value).  workspace:
+ *   unit_mil_loss_workspace_bytes(n_img, max_rows, K).
  * unit_oicr_targets replaces compute_loss_inputs / get_proposal_clusters / label_and_sample_proposals
  *   (:353-408, :308-351): for every class present in gt_vector (ascending == torch.unique order) pick the
  *   image's not-yet-picked proposal with the largest probs[r, c] (first one on ties; picked rows count as 0
@@ -238,9 +240,11 @@ int unit_mask_paste(const float* masks, const float* boxes, int D, int M, int im
  *   [n_img,K] its score.  Images without any present class get labels K and weights 0.
  * unit_weighted_ce_loss replaces weighted_softmax_with_loss (:220-227): loss [1] = mean_r(weights[r] *
  *   cross_entropy(scores[r], labels[r])), d_scores [R,K1] its gradient.  workspace: R floats. */
+size_t unit_mil_loss_workspace_bytes(int n_img, int max_rows, int K);
 int unit_mil_loss(const float* cls_logits, const float* det_logits, const int* img_offsets, const float* gt_vector,
-                  int n_img, int R, int K, float multiplier, float* mil_scores, float* class_vector, float* loss,
-                  float* d_cls, float* d_det, void* workspace, size_t workspace_bytes, unit_stream_t stream);
+                  int n_img, int R, int max_rows, int K, float multiplier, float* mil_scores, float* class_vector,
+                  float* loss, float* d_cls, float* d_det, void* workspace, size_t workspace_bytes,
+                  unit_stream_t stream);
 int unit_oicr_targets(const float* probs, int ld, const float* prop_boxes, const int* prop_offsets,
                       const float* gt_vector, int n_img, int P_total, int K, const float* thresholds_host,
                       const int* labels_host, int T, float bg_threshold, int64_t* labels, float* weights,

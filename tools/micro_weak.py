@@ -28,7 +28,7 @@ def main():
 
     def step():
         c, dd = d['c'].requires_grad_(True), d['d'].requires_grad_(True)
-        loss, probs, _ = ops.mil_loss(c, dd, off, d['gt'], 1.0)
+        loss, probs, _ = ops.mil_loss(c, dd, off, d['gt'], 1.0, max_rows=per)
         total = loss
         for i in range(3):
             if i:

@@ -59,7 +59,8 @@ _SIGNATURES = {
     "unit_predictor_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "unit_predictor_gemm": (c_int, [P, P, P, P, c_int, c_int, c_int, P, c_size_t, P]),
     "unit_boxes_to_rois": (c_int, [P, P, c_int, c_int, P, P]),
-    "unit_mil_loss": (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P, P, P, c_size_t, P]),
+    "unit_mil_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "unit_mil_loss": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P, c_size_t, P]),
     "unit_oicr_targets": (c_int, [P, c_int, P, P, P, c_int, c_int, c_int, P, P, c_int, c_float, P, P, P, P, P]),
     "unit_weighted_ce_loss": (c_int, [P, P, P, c_int, c_int, P, P, P, c_size_t, P]),
 }

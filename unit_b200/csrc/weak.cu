@@ -1,7 +1,8 @@
 // Weak-image training losses of the base stage.
 //
-//   mil_loss_kernel      weak_detector_fast_rcnn.py:189-214  x = softmax_classes(cls) * softmax_proposals(det), the
-//                        image-level BCE on sum_r x (clamped to [eps, 1-eps]) AND its gradients, one CTA per image
+//   mil_*_kernel         weak_detector_fast_rcnn.py:189-214  x = softmax_classes(cls) * softmax_proposals(det), the
+//                        image-level BCE on sum_r x (clamped to [eps, 1-eps]) AND its gradients, in three grid-wide
+//                        phases over 128-row chunks (a single CTA per image took 0.28 ms for 2 x 2000 proposals)
 //   oicr_targets_kernel  :353-408 + :308-351  get_proposal_clusters (per present class, ascending: the proposal with
 //                        the highest score, whose row is then zeroed) -> pairwise_iou + UniT Matcher against those
 //                        pseudo boxes -> refinement labels and per-proposal loss weights, one CTA per image
@@ -20,22 +21,6 @@ constexpr int NT = 1024;
 constexpr int NWARP = NT / 32;
 constexpr int KMAX = 128;  // classes (VOC 20, COCO 80)
 constexpr int KL = KMAX / 32;
-
-// part[warp][k] -> dst[k] = reduce over warps in warp order (deterministic)
-template <bool MAX>
-__device__ __forceinline__ void col_reduce(float (*part)[KMAX], const float (&acc)[KL], float* dst, int K) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int j = 0; j < KL; ++j)
-    if (lane + 32 * j < K) part[warp][lane + 32 * j] = acc[j];
-  __syncthreads();
-  if ((int)threadIdx.x < K) {
-    float v = part[0][threadIdx.x];
-    for (int w = 1; w < NWARP; ++w) v = MAX ? fmaxf(v, part[w][threadIdx.x]) : v + part[w][threadIdx.x];
-    dst[threadIdx.x] = v;
-  }
-  __syncthreads();
-}
 
 __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -66,37 +51,92 @@ __device__ __forceinline__ void row_softmax(const float* __restrict__ row, int K
   for (int j = 0; j < KL; ++j) p[j] = __fdiv_rn(p[j], s);
 }
 
-__global__ void __launch_bounds__(NT) mil_loss_kernel(const float* __restrict__ cls, const float* __restrict__ det,
-                                                      const int* __restrict__ img_off, const float* __restrict__ gt_vec,
-                                                      int K, float scale, float eps, float* __restrict__ mil,
-                                                      float* __restrict__ class_vec, float* __restrict__ img_loss,
-                                                      float* __restrict__ d_cls, float* __restrict__ d_det) {
-  __shared__ float part[NWARP][KMAX];
-  __shared__ float colmax[KMAX], colsum[KMAX], vcol[KMAX], gcol[KMAX], term[KMAX];
-  const int img = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = img_off[img], r1 = img_off[img + 1];
+// ---- MIL loss in three grid-wide phases (one CTA per 128-row chunk of an image; an image's softmax over its
+// proposals needs column statistics of ALL its rows, so the phases are separate launches):
+//   1 mil_colstats_kernel  per chunk and class: max of the detection logits and sum of exp(d - max)
+//   2 mil_scores_kernel    combine the chunk statistics, x = p * q for the chunk's rows, per-chunk class sums
+//   3 mil_grads_kernel     class vector, clamped BCE term, g = dL/dv, both gradients for the chunk's rows
+constexpr int MT = 256;           // threads per CTA
+constexpr int MW = MT / 32;       // warps
+constexpr int MROWS = 128;        // rows per chunk
+
+template <bool MAX>
+__device__ __forceinline__ void chunk_reduce(float (*part)[KMAX], const float (&acc)[KL], float* dst, int K) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < KL; ++j)
+    if (lane + 32 * j < K) part[warp][lane + 32 * j] = acc[j];
+  __syncthreads();
+  if ((int)threadIdx.x < K) {
+    float v = part[0][threadIdx.x];
+    for (int w = 1; w < MW; ++w) v = MAX ? fmaxf(v, part[w][threadIdx.x]) : v + part[w][threadIdx.x];
+    dst[threadIdx.x] = v;
+  }
+  __syncthreads();
+}
+
+// stats [n_img][nch][K][2] = (chunk max, chunk sum of exp(d - chunk max)); an empty chunk writes (-inf, 0)
+__global__ void __launch_bounds__(MT) mil_colstats_kernel(const float* __restrict__ det, const int* __restrict__ img_off,
+                                                          int K, int nch, float* __restrict__ stats) {
+  __shared__ float part[MW][KMAX];
+  __shared__ float cmax[KMAX], csum[KMAX];
+  const int img = blockIdx.y, ch = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = img_off[img] + ch * MROWS, r1 = min(img_off[img + 1], r0 + MROWS);
   float acc[KL];
-  // softmax over the proposals of the image, per class: column max, then column sum
 #pragma unroll
   for (int j = 0; j < KL; ++j) acc[j] = -INFINITY;
-  for (int r = r0 + warp; r < r1; r += NWARP) {
+  for (int r = r0 + warp; r < r1; r += MW) {
 #pragma unroll
     for (int j = 0; j < KL; ++j)
       if (lane + 32 * j < K) acc[j] = fmaxf(acc[j], det[(long long)r * K + lane + 32 * j]);
   }
-  col_reduce<true>(part, acc, colmax, K);
+  chunk_reduce<true>(part, acc, cmax, K);
 #pragma unroll
   for (int j = 0; j < KL; ++j) acc[j] = 0.f;
-  for (int r = r0 + warp; r < r1; r += NWARP) {
+  for (int r = r0 + warp; r < r1; r += MW) {
 #pragma unroll
     for (int j = 0; j < KL; ++j)
-      if (lane + 32 * j < K) acc[j] += expf(det[(long long)r * K + lane + 32 * j] - colmax[lane + 32 * j]);
+      if (lane + 32 * j < K) acc[j] += expf(det[(long long)r * K + lane + 32 * j] - cmax[lane + 32 * j]);
   }
-  col_reduce<false>(part, acc, colsum, K);
-  // x = p * q, class vector
+  chunk_reduce<false>(part, acc, csum, K);
+  if ((int)threadIdx.x < K) {
+    float* o = stats + (((long long)img * nch + ch) * K + threadIdx.x) * 2;
+    o[0] = cmax[threadIdx.x];
+    o[1] = csum[threadIdx.x];
+  }
+}
+
+// column max / sum of an image from its chunk statistics, in chunk order (deterministic)
+__device__ __forceinline__ void combine_stats(const float* __restrict__ stats, int img, int nch, int K, float* colmax,
+                                              float* colsum) {
+  if ((int)threadIdx.x < K) {
+    const float* s = stats + ((long long)img * nch * K + threadIdx.x) * 2;
+    float m = -INFINITY;
+    for (int c = 0; c < nch; ++c) m = fmaxf(m, s[(long long)c * K * 2]);
+    float t = 0.f;
+    for (int c = 0; c < nch; ++c) {
+      const float cm = s[(long long)c * K * 2], cs = s[(long long)c * K * 2 + 1];
+      if (cs != 0.f) t += cs * expf(cm - m);
+    }
+    colmax[threadIdx.x] = m;
+    colsum[threadIdx.x] = t;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(MT) mil_scores_kernel(const float* __restrict__ cls, const float* __restrict__ det,
+                                                        const int* __restrict__ img_off, const float* __restrict__ stats,
+                                                        int K, int nch, float* __restrict__ mil,
+                                                        float* __restrict__ vpart) {
+  __shared__ float part[MW][KMAX];
+  __shared__ float colmax[KMAX], colsum[KMAX], vsum[KMAX];
+  const int img = blockIdx.y, ch = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = img_off[img] + ch * MROWS, r1 = min(img_off[img + 1], r0 + MROWS);
+  combine_stats(stats, img, nch, K, colmax, colsum);
+  float acc[KL];
 #pragma unroll
   for (int j = 0; j < KL; ++j) acc[j] = 0.f;
-  for (int r = r0 + warp; r < r1; r += NWARP) {
+  for (int r = r0 + warp; r < r1; r += MW) {
     float p[KL];
     row_softmax(cls + (long long)r * K, K, lane, p);
 #pragma unroll
@@ -110,24 +150,39 @@ __global__ void __launch_bounds__(NT) mil_loss_kernel(const float* __restrict__ 
       }
     }
   }
-  col_reduce<false>(part, acc, vcol, K);
-  // binary cross-entropy on the clamped class vector and dL/dv
+  chunk_reduce<false>(part, acc, vsum, K);
+  if ((int)threadIdx.x < K) vpart[((long long)img * nch + ch) * K + threadIdx.x] = vsum[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(MT) mil_grads_kernel(const float* __restrict__ cls, const float* __restrict__ det,
+                                                       const int* __restrict__ img_off, const float* __restrict__ gt_vec,
+                                                       const float* __restrict__ stats, const float* __restrict__ vpart,
+                                                       int K, int nch, float scale, float eps,
+                                                       float* __restrict__ class_vec, float* __restrict__ img_loss,
+                                                       float* __restrict__ d_cls, float* __restrict__ d_det) {
+  __shared__ float colmax[KMAX], colsum[KMAX], vcol[KMAX], gcol[KMAX], term[KMAX];
+  const int img = blockIdx.y, ch = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = img_off[img] + ch * MROWS, r1 = min(img_off[img + 1], r0 + MROWS);
+  if (ch > 0 && r0 >= r1) return;  // chunk 0 always runs: it owns the image's class vector and loss term
   if ((int)threadIdx.x < K) {
     const int k = threadIdx.x;
-    const float v = vcol[k], y = gt_vec[(long long)img * K + k];
-    class_vec[(long long)img * K + k] = v;
+    float v = 0.f;
+    for (int c = 0; c < nch; ++c) v += vpart[((long long)img * nch + c) * K + k];
+    const float y = gt_vec[(long long)img * K + k];
     const float vc = fminf(fmaxf(v, eps), 1.f - eps);
+    vcol[k] = v;
     term[k] = -(y * fmaxf(logf(vc), -100.f) + (1.f - y) * fmaxf(log1pf(-vc), -100.f));
     gcol[k] = (v >= eps && v <= 1.f - eps) ? scale * ((1.f - y) / (1.f - vc) - y / vc) : 0.f;
+    if (ch == 0) class_vec[(long long)img * K + k] = v;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  combine_stats(stats, img, nch, K, colmax, colsum);  // ends with a barrier: vcol / gcol / term are visible too
+  if (ch == 0 && threadIdx.x == 0) {
     float t = 0.f;
     for (int k = 0; k < K; ++k) t += term[k];
     img_loss[img] = t * scale;
   }
   // gradients: d_det = g q (p - v),  d_cls = p (g q - sum_k g_k x_k)
-  for (int r = r0 + warp; r < r1; r += NWARP) {
+  for (int r = r0 + warp; r < r1; r += MW) {
     float p[KL], q[KL];
     row_softmax(cls + (long long)r * K, K, lane, p);
     float t = 0.f;
@@ -292,23 +347,41 @@ using namespace unit;
 
 extern "C" {
 
+size_t unit_mil_loss_workspace_bytes(int n_img, int max_rows, int K) {
+  const size_t nch = (size_t)((max_rows > 0 ? max_rows : 1) + weak::MROWS - 1) / weak::MROWS;
+  return ((size_t)n_img * nch * K * 3 + (size_t)n_img) * sizeof(float);
+}
+
 int unit_mil_loss(const float* cls_logits, const float* det_logits, const int* img_offsets, const float* gt_vector,
-                  int n_img, int R, int K, float multiplier, float* mil_scores, float* class_vector, float* loss,
-                  float* d_cls, float* d_det, void* workspace, size_t workspace_bytes, unit_stream_t stream) {
+                  int n_img, int R, int max_rows, int K, float multiplier, float* mil_scores, float* class_vector,
+                  float* loss, float* d_cls, float* d_det, void* workspace, size_t workspace_bytes,
+                  unit_stream_t stream) {
   UNIT_REQUIRE(n_img > 0 && R >= 0 && K > 0 && K <= weak::KMAX, "mil_loss: bad shape (K <= %d)", weak::KMAX);
+  UNIT_REQUIRE(max_rows >= 0 && max_rows <= R, "mil_loss: max_rows must be the largest per-image row count");
   UNIT_REQUIRE(img_offsets && gt_vector && class_vector && loss, "mil_loss: null pointer");
   UNIT_REQUIRE(R == 0 || (cls_logits && det_logits && mil_scores && d_cls && d_det), "mil_loss: null pointer");
-  if (!workspace || workspace_bytes < (size_t)n_img * sizeof(float)) {
+  if (!workspace || workspace_bytes < unit_mil_loss_workspace_bytes(n_img, max_rows, K)) {
     set_error("mil_loss: workspace too small");
     return UNIT_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  const int nch = ((max_rows > 0 ? max_rows : 1) + weak::MROWS - 1) / weak::MROWS;
+  UNIT_REQUIRE(n_img <= 65535, "mil_loss: at most 65535 images per call");
+  float* stats = (float*)workspace;                       // [n_img][nch][K][2]
+  float* vpart = stats + (size_t)n_img * nch * K * 2;      // [n_img][nch][K]
+  float* img_loss = vpart + (size_t)n_img * nch * K;       // [n_img]
   // F.binary_cross_entropy 'mean' over the [n_img, K] class vectors, times MIL_MULTIPLIER
   const float scale = multiplier / ((float)n_img * (float)K);
-  weak::mil_loss_kernel<<<n_img, weak::NT, 0, st>>>(cls_logits, det_logits, img_offsets, gt_vector, K, scale, 1e-6f,
-                                                     mil_scores, class_vector, (float*)workspace, d_cls, d_det);
-  UNIT_CHECK_LAUNCH("mil_loss_kernel");
-  weak::sum_kernel<<<1, 256, 0, st>>>((const float*)workspace, n_img, 1.f, loss);
+  dim3 grid(nch, n_img);
+  weak::mil_colstats_kernel<<<grid, weak::MT, 0, st>>>(det_logits, img_offsets, K, nch, stats);
+  UNIT_CHECK_LAUNCH("mil_colstats_kernel");
+  weak::mil_scores_kernel<<<grid, weak::MT, 0, st>>>(cls_logits, det_logits, img_offsets, stats, K, nch, mil_scores,
+                                                      vpart);
+  UNIT_CHECK_LAUNCH("mil_scores_kernel");
+  weak::mil_grads_kernel<<<grid, weak::MT, 0, st>>>(cls_logits, det_logits, img_offsets, gt_vector, stats, vpart, K,
+                                                     nch, scale, 1e-6f, class_vector, img_loss, d_cls, d_det);
+  UNIT_CHECK_LAUNCH("mil_grads_kernel");
+  weak::sum_kernel<<<1, 256, 0, st>>>(img_loss, n_img, 1.f, loss);
   UNIT_CHECK_LAUNCH("sum_kernel");
   return UNIT_OK;
 }

@@ -345,7 +345,7 @@ class _MILLossFn(torch.autograd.Function):
     """weak_detector_fast_rcnn.py:189-214 fused with its gradient: (loss_im_cls, mil_scores, class_vector)."""
 
     @staticmethod
-    def forward(ctx, cls_logits, det_logits, img_offsets, gt_vector, multiplier):
+    def forward(ctx, cls_logits, det_logits, img_offsets, gt_vector, multiplier, max_rows):
         dev = _need_cuda(cls_logits, det_logits, img_offsets, gt_vector)
         cls_logits, det_logits = _c(cls_logits, _F32), _c(det_logits, _F32)
         gt_vector = _c(gt_vector, _F32)
@@ -355,10 +355,11 @@ class _MILLossFn(torch.autograd.Function):
         class_vec = torch.empty((n_img, K), dtype=_F32, device=dev)
         loss = torch.empty((1,), dtype=_F32, device=dev)
         d_cls, d_det = torch.empty_like(mil), torch.empty_like(mil)
-        ws = _workspace(dev, max(n_img, 1) * 4)
-        check(lib().unit_mil_loss(_ptr(cls_logits), _ptr(det_logits), _ptr(img_offsets), _ptr(gt_vector), n_img, R, K,
-                                  float(multiplier), _ptr(mil), _ptr(class_vec), _ptr(loss), _ptr(d_cls), _ptr(d_det),
-                                  _ptr(ws), ws.numel(), _stream()), "unit_mil_loss")
+        max_rows = R if max_rows is None else min(int(max_rows), R)
+        ws = _workspace(dev, lib().unit_mil_loss_workspace_bytes(n_img, max_rows, K))
+        check(lib().unit_mil_loss(_ptr(cls_logits), _ptr(det_logits), _ptr(img_offsets), _ptr(gt_vector), n_img, R,
+                                  max_rows, K, float(multiplier), _ptr(mil), _ptr(class_vec), _ptr(loss), _ptr(d_cls),
+                                  _ptr(d_det), _ptr(ws), ws.numel(), _stream()), "unit_mil_loss")
         ctx.save_for_backward(d_cls, d_det)
         ctx.mark_non_differentiable(mil, class_vec)
         return loss[0], mil, class_vec
@@ -366,12 +367,14 @@ class _MILLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, _g_mil, _g_vec):
         d_cls, d_det = ctx.saved_tensors
-        return d_cls * g_loss, d_det * g_loss, None, None, None
+        return d_cls * g_loss, d_det * g_loss, None, None, None, None
 
 
-def mil_loss(cls_logits, det_logits, img_offsets, gt_vector, multiplier: float = 1.0):
-    """-> (loss_im_cls scalar, mil_scores [R,K] detached, class_vector [n_img,K] detached)."""
-    return _MILLossFn.apply(cls_logits, det_logits, img_offsets, gt_vector, float(multiplier))
+def mil_loss(cls_logits, det_logits, img_offsets, gt_vector, multiplier: float = 1.0,
+             max_rows: Optional[int] = None):
+    """-> (loss_im_cls scalar, mil_scores [R,K] detached, class_vector [n_img,K] detached).  ``max_rows``: the largest
+    per-image proposal count when the caller knows it on the host (sizes the grid; default: all rows)."""
+    return _MILLossFn.apply(cls_logits, det_logits, img_offsets, gt_vector, float(multiplier), max_rows)
 
 
 def oicr_targets(probs: torch.Tensor, prop_boxes: torch.Tensor, prop_offsets: torch.Tensor, gt_vector: torch.Tensor,

@@ -187,10 +187,12 @@ class WeakDetectorOutputsBase(nn.Module):
         (weak_detector_fast_rcnn.py:218-228, 384-396), plus the image-level MIL loss they start from."""
         cls_stream, det_stream, oicr_scores = weak_predictions[0], weak_predictions[1], weak_predictions[2]
         dev = cls_stream.device
-        offsets = ops.offsets_from_counts([len(p) for p in weak_proposals], dev)
+        counts = [len(p) for p in weak_proposals]
+        offsets = ops.offsets_from_counts(counts, dev)
         boxes = layers.cat([p.proposal_boxes.tensor for p in weak_proposals])
         gt_vector = self.image_label_vector(weak_targets, dev)
-        loss_im, probs, _ = ops.mil_loss(cls_stream, det_stream, offsets, gt_vector, self.mil_multiplier)
+        loss_im, probs, _ = ops.mil_loss(cls_stream, det_stream, offsets, gt_vector, self.mil_multiplier,
+                                         max_rows=max(counts) if counts else 0)
         supervision = []
         with torch.no_grad():
             for idx in range(len(oicr_scores)):
