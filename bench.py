@@ -621,7 +621,7 @@ def run_ours(args):
             aux["weak_losses"] = {
                 "ms_per_call": time_kernel(weak_path, 10, flush),
                 "what": "MIL image loss + 3 x (OICR pseudo-labelling + weighted CE) with gradients, 2 images x 2000 "
-                        "proposals, K=20: 13 launches, eager, CUDA events"}
+                        "proposals, K=20: 15 launches, eager, CUDA events"}
             wl.head.train()
 
     # CPU baseline on the box's host cores (rank 0, N = 1 only): the oracle port on a bounded sample
