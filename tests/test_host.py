@@ -187,6 +187,26 @@ def test_c_abi_exports_every_declared_symbol():
     assert lib.unit_nms_workspace_bytes(2, 1000) > 36 * 2000
 
 
+def test_transfer_params_struct_matches_the_header():
+    """The one struct that crosses the ABI: same fields, same order, same C types in include/unit_b200.h and in the
+    ctypes mirror (a silent drift would shift every later field)."""
+    from unit_b200._lib import TransferParams
+
+    hdr = open(os.path.join(ROOT, "include", "unit_b200.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\} unit_transfer_params;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, names = decl.split(None, 1)
+        fields += [(n.strip(), ctype) for n in names.split(",")]
+    want = [(n, {"c_int": "int", "c_float": "float"}[t.__name__]) for n, t in TransferParams._fields_]
+    assert fields == want
+    assert ctypes.sizeof(TransferParams) == 4 * len(fields)
+
+
 def test_product_never_imports_oracle():
     for f in glob.glob(os.path.join(ROOT, "unit_b200", "*.py")):
         src = open(f).read()
