@@ -207,6 +207,44 @@ def test_transfer_params_struct_matches_the_header():
     assert ctypes.sizeof(TransferParams) == 4 * len(fields)
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/unit_b200.h against unit_b200._lib._SIGNATURES: same argument count and the same
+    class of C type (pointer / int / float / 64-bit unsigned) in every position, same return type."""
+    from unit_b200 import _lib
+
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "unit_b200.h")).read(), flags=re.S)
+    protos = re.findall(r"^\s*((?:const\s+)?[\w ]+?\**)\s*(unit_\w+)\s*\(([^;{]*?)\)\s*;", hdr, re.M)
+    assert len(protos) >= 30
+
+    def c_kind(decl):
+        decl = decl.strip()
+        if "*" in decl or decl.startswith("unit_stream_t"):
+            return "ptr"
+        base = decl.replace("const", "").split()
+        base = " ".join(base[:-1]) if len(base) > 1 else base[0]
+        return {"int": "int", "float": "float", "size_t": "u64", "unsigned long long": "u64"}[base]
+
+    def ct_kind(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) is None:
+            return "ptr"
+        # c_size_t and c_ulonglong are the same 8-byte class on this ABI (ctypes aliases them)
+        return {ctypes.c_int: "int", ctypes.c_float: "float", ctypes.c_size_t: "u64",
+                ctypes.c_ulonglong: "u64"}.get(t, "ptr")
+
+    seen = set()
+    for ret, name, params in protos:
+        assert name in _lib._SIGNATURES, name
+        seen.add(name)
+        restype, argtypes = _lib._SIGNATURES[name]
+        plist = [] if params.strip() in ("", "void") else [p for p in params.split(",")]
+        assert len(plist) == len(argtypes), (name, len(plist), len(argtypes))
+        for i, (decl, t) in enumerate(zip(plist, argtypes)):
+            assert c_kind(decl) == ct_kind(t), (name, i, decl.strip(), t)
+        want_ret = "ptr" if "*" in ret else {"int": "int", "size_t": "u64", "unsigned long long": "u64"}[ret.strip()]
+        assert ct_kind(restype) == want_ret, (name, ret)
+    assert seen == set(_lib._SIGNATURES), set(_lib._SIGNATURES) ^ seen
+
+
 def test_product_never_imports_oracle():
     for f in glob.glob(os.path.join(ROOT, "unit_b200", "*.py")):
         src = open(f).read()
