@@ -245,6 +245,25 @@ def test_ctypes_signatures_match_the_header_prototypes():
     assert seen == set(_lib._SIGNATURES), set(_lib._SIGNATURES) ^ seen
 
 
+def test_weak_head_image_label_vector():
+    """The multi-hot image labels that drive both the MIL loss and the OICR class order: non-zero columns in ascending
+    order == torch.unique(gt_classes) of the reference (weak_detector_fast_rcnn.py:203,213-216)."""
+    from unit_b200.config import load_cfg
+    from unit_b200.predictors import WeakDetectorOutputsBase
+    from unit_b200.structures import ShapeSpec
+
+    cfg = load_cfg(os.path.join(ROOT, "configs", "voc_split1_base.yaml"),
+                   ["MODEL.ROI_HEADS.EMBEDDING_PATH", os.path.join(ROOT, "tests", "golden", "glove_mean.pt")])
+    wd = WeakDetectorOutputsBase(cfg, ShapeSpec(channels=8))
+    assert wd.weak_detector_type == "OICR" and wd.oicr_iter == 3 and wd.bg_threshold == 0.1
+    targets = [torch.tensor([3, 7, 3, 11]), torch.tensor([], dtype=torch.int64), torch.tensor([19, 0, 8, 8])]
+    v = wd.image_label_vector(targets, torch.device("cpu"))
+    assert v.shape == (3, 20) and v.dtype == torch.float32
+    for row, t in zip(v, targets):
+        assert torch.equal(row.nonzero().flatten(), torch.unique(t))
+    assert set(v.unique().tolist()) <= {0.0, 1.0}
+
+
 def test_product_never_imports_oracle():
     for f in glob.glob(os.path.join(ROOT, "unit_b200", "*.py")):
         src = open(f).read()
