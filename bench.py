@@ -345,6 +345,12 @@ def cpu_reference_step(host_set, weights, head_meta, gen, x, xw, grad_pooled, ro
     loss = loss_cls + (bbox[fg[:, None], cols] - tgt).abs().sum() / gt_classes.numel()
     loss.backward()
     t_pred = time.perf_counter() - t0
+    cpu_reference_step.last = {  # everything the parity test at bench shapes compares (tests/test_bench_config_gpu.py)
+        "sampled_boxes": s_boxes, "sampled_classes": s_cls, "sampled_gt": s_gt, "rois": rois, "scores": scores.detach(),
+        "bbox": bbox.detach(), "loss_cls": loss_cls.detach(), "loss": loss.detach(),
+        "grads": {k: w[k].grad for k in ("cls_score_ft.weight", "cls_score_ft.bias", "bbox_pred_ft.weight",
+                                         "bbox_pred_ft.bias")},
+    }
     return float(loss.detach()), t_label, t_roi, t_pred, pooled, gfeat
 
 

@@ -36,6 +36,9 @@ enum { UNIT_F32 = 0, UNIT_BF16 = 1 };
 
 int unit_version(void);
 const char* unit_last_error(void);
+/* sha256 of the sources (csrc/, this header, compile flags) the library was built from; the Python loader refuses a
+ * library whose digest differs from the tree it sits in. */
+const char* unit_source_digest(void);
 /* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
 unsigned long long unit_launch_count(void);
 
@@ -198,6 +201,15 @@ int unit_similarity_transfer_bwd(const unit_transfer_params* p, const float* s_c
                                  const int* base, const int* novel, const int* class_kind, const float* g_scores,
                                  const float* g_bbox, int detach_transfer, float* g_delta_scores,
                                  float* g_proposal_deltas, unit_stream_t stream);
+
+/* Gradient of the same fused step w.r.t. the visual logits (the mean OICR logits the visual similarity is built from).
+ * The reference's get_similarity_matrices (modeling/roi_heads/roi_heads.py:245-257, called at :618) is not under
+ * no_grad, so with a trainable box head the fine-tune loss reaches box_features through softmax -> renormalise ->
+ * threshold -> S -> bmm (fast_rcnn.py:503-516).  Inputs are the forward's; g_vis_logits is [R,K+1]. */
+int unit_similarity_transfer_bwd_vis(const unit_transfer_params* p, const float* vis_logits, const float* static_cls,
+                                     const float* static_bbox, const int* base, const int* novel,
+                                     const float* delta_scores, const float* proposal_deltas, const float* g_scores,
+                                     const float* g_bbox, float* g_vis_logits, unit_stream_t stream);
 
 /* Predictor GEMM on tcgen05 tensor cores: y[M,N] = x[M,K] . w[N,K]^T + bias[N], fp32 in / fp32 out, TF32 multiply
  * with fp32 accumulation in TMEM (TMA-fed, split-K with a deterministic reduction).  Replaces the packed nn.Linear

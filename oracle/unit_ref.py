@@ -1,7 +1,7 @@
 """Oracle restatement of the UniT side of the RoI stage (functional, CPU, fp32).  TEST INFRASTRUCTURE.
 
 Every function cites the reference lines it follows.  It is pinned against the reference's own files executed
-verbatim (oracle.shim) by tests/test_oracle_vs_reference.py and against the committed fixtures in tests/golden/.
+verbatim (oracle.shim) by tests/test_oracle.py and against the committed fixtures in tests/golden/.
 Weights are passed as a flat dict keyed by the reference's state_dict names (SURVEY.md section 5 "Checkpoint"):
   cls_score_delta.{weight,bias}  bbox_pred_delta.{weight,bias}  cls_score_ft.*  bbox_pred_ft.*
   weak_detector_head.oicr_predictors.{0,1,2}.{weight,bias}  embeddings.weight

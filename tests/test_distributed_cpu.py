@@ -51,3 +51,19 @@ def test_world_size_2_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def test_flat_bucket_survives_zero_grad():
+    """zero_grad(set_to_none=True) drops the views; all_reduce_mean must refuse, zero_() must re-bind."""
+    from unit_b200.distributed import FlatGradBucket
+
+    lin = torch.nn.Linear(4, 3)
+    bucket = FlatGradBucket(lin.parameters())
+    lin.zero_grad(set_to_none=True)
+    with pytest.raises(RuntimeError, match="no longer a view"):
+        bucket.all_reduce_mean()
+    bucket.zero_()
+    lin(torch.ones(2, 4)).sum().backward()
+    assert lin.weight.grad.data_ptr() == bucket.flat.data_ptr()
+    assert torch.equal(bucket.flat[:12].view(3, 4), torch.full((3, 4), 2.0))
+    bucket.all_reduce_mean()  # single process: nothing to reduce, but the views are verified

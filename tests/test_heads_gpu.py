@@ -442,3 +442,56 @@ def test_mask_head_inference_coco(registry):
 
     out = detector_postprocess(inst, 800, 1344)
     assert out.pred_masks.dtype == torch.bool and out.pred_masks.shape[1:] == (800, 1344)
+
+
+def test_finetune_similarity_gradient_reaches_box_features(registry):
+    """the reference builds the similarity with autograd on (roi_heads.py:245-257, 618), so with a
+    trainable box head dL/dbox_features includes the path softmax -> renormalise -> threshold -> S -> bmm.  fp32 GEMMs
+    on both sides; gradient w.r.t. x (which would flow on into box_head) vs the CPU oracle's autograd."""
+    from oracle import unit_ref
+
+    _StandInBoxHead.OUT = 96
+    try:
+        cfg, head = _build("voc_split1_ft.yaml", 16, registry)
+    finally:
+        _StandInBoxHead.OUT = 64
+    g = seeded(808)
+    with torch.no_grad():
+        for name, p in sorted(head.box_predictor.named_parameters()):
+            if not name.startswith("embeddings"):
+                p.copy_(torch.randn(p.shape, generator=g) * (0.05 if "bbox" in name else 0.3))
+    head = head.cuda().train()
+    head.move_mappings_to_gpu()
+    R, K = 300, 20
+    x0 = torch.relu(torch.randn(R, 96, generator=g))
+    xw = torch.relu(torch.randn(R, 96, generator=g))
+    gs = torch.randn(R, K + 1, generator=g)
+    gb = torch.randn(R, 4 * K, generator=g)
+    x = x0.clone().cuda().requires_grad_(True)
+    sim = head.get_similarity_matrices(x)
+    assert sim.vis_logits.requires_grad
+    (scores, bbox), _ = head.box_predictor(x, supervised_branch_x_weak=xw.cuda(),
+                                           novel_classes=head._novel_classes_tensor,
+                                           base_classes=head._base_classes_tensor, similarity=sim)
+    ((scores * gs.cuda()).sum() + (bbox * gb.cuda()).sum()).backward()
+    # oracle
+    w = {k: v.detach().cpu() for k, v in head.box_predictor.state_dict().items()}
+    base, novel = head._base_classes_tensor.cpu(), head._novel_classes_tensor.cpu()
+    xr = x0.clone().requires_grad_(True)
+    L = unit_ref.lingual_similarity(w["embeddings.weight"], head._coco_indexer_tensor.cpu(), base, novel)
+    V = unit_ref.visual_similarity(unit_ref.oicr_mean_logits(xr, w), base, head.visual_threshold)
+    rsim = unit_ref.similarity_matrices(L, V, {k: list(v) for k, v in head.terms.items()}, 5, 15)
+    rs, rb = unit_ref.predictor_forward(xr, xw, w, rsim, base, novel, K, kind="FineTune", training=True)
+    ((rs * gs).sum() + (rb * gb).sum()).backward()
+    # and the same with the similarity detached: the difference is the path this test is about
+    xd = x0.clone().requires_grad_(True)
+    dsim = {k: v.detach() for k, v in rsim.items()}
+    ds, db = unit_ref.predictor_forward(xd, xw, w, dsim, base, novel, K, kind="FineTune", training=True)
+    ((ds * gs).sum() + (db * gb).sum()).backward()
+    through_sim = (xr.grad - xd.grad)
+    assert through_sim.abs().max() > 1e-3 * xr.grad.abs().max(), "test is vacuous: no gradient through the similarity"
+    assert_close_rms(scores.detach().cpu(), rs.detach(), 2e-5, "scores")
+    assert_close_rms(x.grad.cpu(), xr.grad, 1e-4, "dL/dx incl. the similarity path")
+    # frozen features (the shipped VOC split-1 setting): no graph is built through the similarity
+    sim2 = head.get_similarity_matrices(x0.cuda())
+    assert not sim2.vis_logits.requires_grad

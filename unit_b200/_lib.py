@@ -29,6 +29,7 @@ P = c_void_p
 _SIGNATURES = {
     "unit_version": (c_int, []),
     "unit_last_error": (c_char_p, []),
+    "unit_source_digest": (c_char_p, []),
     "unit_launch_count": (c_ulonglong, []),
     "unit_roi_align_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "unit_roi_align_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
@@ -54,6 +55,7 @@ _SIGNATURES = {
     "unit_lingual_similarity": (c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P]),
     "unit_similarity_transfer": (c_int, [POINTER(TransferParams)] + [P] * 17 + [P]),
     "unit_similarity_transfer_bwd": (c_int, [POINTER(TransferParams), P, P, P, P, P, P, P, c_int, P, P, P]),
+    "unit_similarity_transfer_bwd_vis": (c_int, [POINTER(TransferParams)] + [P] * 10 + [P]),
     "unit_mask_transfer": (c_int, [P, P, c_int, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "unit_mask_paste": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, P, P]),
     "unit_predictor_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
@@ -82,13 +84,20 @@ def lib() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH) and "UNIT_B200_LIB" not in os.environ:
-        # the library normally travels with the tree; a bare source checkout on a box with nvcc builds it once
-        try:
-            from . import build as _build
-            _build.build()
-        except Exception:  # no nvcc / compile error: fall through to the explicit failure below
-            pass
+    if "UNIT_B200_LIB" not in os.environ:
+        # The library normally travels with the tree.  It carries the digest of the sources it was built from: a
+        # missing or STALE library (sources changed after a pull) is rebuilt when nvcc is present, and a stale one
+        # that cannot be rebuilt is refused instead of silently running old kernels behind a new ABI.
+        from . import build as _build
+        want, have = _build.source_digest(), _build.embedded_digest(LIB_PATH)
+        if have != want:
+            try:
+                _build.build()
+            except Exception as e:  # no nvcc / compile error
+                if os.path.exists(LIB_PATH):
+                    raise UnitLibraryError(
+                        f"{LIB_PATH} was built from other sources (digest {have}, csrc/ is {want}) and could not be "
+                        f"rebuilt: {e}") from e
     if not os.path.exists(LIB_PATH):
         raise UnitLibraryError(
             f"{LIB_PATH} is missing: build it with `python -m unit_b200.build` (needs nvcc). "

@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libunit_b200.so")
-STAMP = os.path.join(HERE, ".libunit_b200.stamp")
+STAMP = os.path.join(HERE, ".libunit_b200.stamp")  # git-ignored convenience only; the .so carries its own digest
 SOURCES = ["api.cu", "roi_align.cu", "roi_align_fwd.cu", "roi_align_fwd_band.cu", "roi_align_bwd.cu", "roi_align_bwd_cl.cu", "match.cu", "detect.cu", "transfer.cu", "gemm.cu", "weak.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -31,7 +31,9 @@ def _nvcc() -> str:
     return cand
 
 
-def _digest() -> str:
+def source_digest() -> str:
+    """sha256 over csrc/, the public header and the compile flags.  It is compiled into the library
+    (``unit_source_digest()``), so ``_lib.lib()`` can tell a stale .so from a fresh one without any side file."""
     h = hashlib.sha256()
     files = sorted(os.listdir(CSRC)) + ["../../include/unit_b200.h"]
     for f in files:
@@ -43,9 +45,23 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def embedded_digest(path: str = LIB):
+    """Digest compiled into an existing library, or None (missing / pre-digest build).  Read from the file's bytes
+    (marker string), not through dlopen: a stale library must not be mapped before it is replaced."""
+    if not os.path.exists(path):
+        return None
+    marker = b"UNIT_SOURCE_DIGEST="
+    with open(path, "rb") as f:
+        blob = f.read()
+    i = blob.find(marker)
+    if i < 0:
+        return None
+    return blob[i + len(marker): i + len(marker) + 64].decode("ascii", "replace")
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
+    digest = source_digest()
+    if not force and embedded_digest() == digest:
         return LIB
     nvcc = _nvcc()
     objdir = os.path.join(HERE, "build")
@@ -56,7 +72,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if not os.path.exists(sp):
             continue
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", obj]
+        extra = [f'-DUNIT_SOURCE_DIGEST="{digest}"'] if src == "api.cu" else []
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for src, obj, pr in procs:

@@ -1,6 +1,7 @@
 // Library-level entry points: version, thread-local error text, launch counter.
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -32,6 +33,29 @@ int sm_count() {
   return cached;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+const Switches& switches() {
+  static const Switches s = [] {
+    Switches v;
+    v.filter_single = getenv("UNIT_FILTER_SINGLE") != nullptr;
+    v.nms_single = getenv("UNIT_NMS_SINGLE") != nullptr;
+    v.fwd_band_bf16 = getenv("UNIT_ROI_FWD_BAND_BF16") != nullptr;
+    v.fwd_v3 = getenv("UNIT_ROI_FWD_V3") != nullptr;
+    v.bwd_v4 = getenv("UNIT_ROI_BWD_V4") != nullptr;
+    v.paste_flat = getenv("UNIT_PASTE_FLAT") != nullptr;
+    v.roi_debug = env_int("UNIT_ROI_DEBUG", 0);
+    v.bwd_promo = env_int("UNIT_ROI_BWD_PROMO", 2);
+    v.bwd_evict_first = env_int("UNIT_ROI_BWD_EVICT_FIRST", 1);
+    v.bwd_sweep3 = env_int("UNIT_ROI_BWD_SWEEP3", 1);
+    return v;
+  }();
+  return s;
+}
+
 }  // namespace unit
 
 extern "C" {
@@ -39,6 +63,12 @@ extern "C" {
 int unit_version(void) { return 100; }  // 0.1.0
 
 const char* unit_last_error(void) { return unit::g_err; }
+
+#ifndef UNIT_SOURCE_DIGEST
+#define UNIT_SOURCE_DIGEST "unknown"
+#endif
+static const char g_digest[] = "UNIT_SOURCE_DIGEST=" UNIT_SOURCE_DIGEST;  // marker read by build.embedded_digest
+const char* unit_source_digest(void) { return g_digest + 19; }
 
 unsigned long long unit_launch_count(void) { return unit::g_launches.load(std::memory_order_relaxed); }
 

@@ -43,6 +43,13 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 int sm_count();
 
+// Developer switches (kernel-variant experiments), read from the environment ONCE per process -- never on a launch path.
+struct Switches {
+  bool filter_single, nms_single, fwd_band_bf16, fwd_v3, bwd_v4, paste_flat;
+  int roi_debug, bwd_promo, bwd_evict_first, bwd_sweep3;
+};
+const Switches& switches();
+
 // IoU with every operation individually rounded to fp32 (the CPU oracle has no FMA contraction):
 //   inter / ((area_a + area_b) - inter), guarded by inter > 0  ([D2] pairwise_iou / [TV] nms).
 __device__ __forceinline__ float box_area_rn(float x1, float y1, float x2, float y2) {

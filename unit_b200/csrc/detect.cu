@@ -944,7 +944,7 @@ int unit_detect_filter(const float* boxes, const float* probs, const int* roi_of
                "detect_filter: null pointer");
   UNIT_REQUIRE((((uintptr_t)boxes | (uintptr_t)cand_boxes) & 15) == 0, "detect_filter: boxes must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (workspace && workspace_bytes >= (size_t)R * 8 + 256 && R > 0 && !getenv("UNIT_FILTER_SINGLE")) {
+  if (workspace && workspace_bytes >= (size_t)R * 8 + 256 && R > 0 && !switches().filter_single) {
     // three small launches spread over the GPU (rows -> counts, per-image scans, rows -> candidates)
     int* row_valid = (int*)workspace;
     int* row_cnt = row_valid + R;
@@ -1000,7 +1000,7 @@ int unit_detect_nms(const float* cand_boxes, const float* cand_scores, const int
   p.cand_roi = cand_roi;
   p.det_stride = topk;
   const long long total = (long long)R * K;
-  if (K >= 2 && cand_cls && total < (1ll << 17) * 64 && !getenv("UNIT_NMS_SINGLE")) {
+  if (K >= 2 && cand_cls && total < (1ll << 17) * 64 && !switches().nms_single) {
     // grouped path: NG CTAs per image + a top-k kernel; images it cannot take fall through to the segmented kernel
     const size_t need = unit_nms_workspace_bytes(n_img, (int)total);
     if (!workspace || workspace_bytes < need) {

@@ -160,8 +160,8 @@ int unit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, in
   UNIT_REQUIRE(feat && rois && out, "roi_align_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (rois_sorted && PH == 14 && PW == 14 && N > 0 && fwd_band_fits(C, H, W, dtype) &&
-      (dtype == UNIT_F32 || getenv("UNIT_ROI_FWD_BAND_BF16")) &&
-      !getenv("UNIT_ROI_FWD_V3")) {  // bf16 I/O: the pair-interleaved kernel below loads its slab faster
+      (dtype == UNIT_F32 || switches().fwd_band_bf16) &&
+      !switches().fwd_v3) {  // bf16 I/O: the pair-interleaved kernel below loads its slab faster
     const size_t need = offsets_bytes(N) + fwd_band_workspace_bytes(R);
     if (!workspace || workspace_bytes < need) {
       set_error("roi_align_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -220,7 +220,7 @@ int unit_roi_align_bwd(const void* grad_out, const float* rois, void* grad_feat,
     UNIT_CUDA(cudaMemsetAsync(grad_feat, 0, (size_t)N * C * H * W * esz, st));
     return UNIT_OK;
   }
-  if (PH == 14 && PW == 14 && bwd_cl_fits(C, H, W, R, dtype, grad_out) && !getenv("UNIT_ROI_BWD_V4")) {
+  if (PH == 14 && PW == 14 && bwd_cl_fits(C, H, W, R, dtype, grad_out) && !switches().bwd_v4) {
     const size_t need = offsets_bytes(N) + bwd_slab2_workspace_bytes(N, C, H, W, dtype);
     if (!workspace || workspace_bytes < need) {
       set_error("roi_align_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);

@@ -600,8 +600,7 @@ int launch_bwd_cl(const void* gout, const float* rois, void* gfeat, void* ws, in
     cuuint64_t strides[1] = {(cuuint64_t)(P * P) * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)(bf ? BF_BOX_ELEMS : CHUNK_F), (cuuint32_t)(bf ? CB / 2 : CB)};
     cuuint32_t estr[2] = {1, 1};
-    const char* ep = getenv("UNIT_ROI_BWD_PROMO");
-    const int promo = ep ? atoi(ep) : 2;
+    const int promo = switches().bwd_promo;
     const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                                      : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                      : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
@@ -624,12 +623,8 @@ int launch_bwd_cl(const void* gout, const float* rois, void* gfeat, void* ws, in
   p.scale = scale;
   p.sampling_ratio = sr;
   p.aligned = aligned;
-  {
-    const char* e = getenv("UNIT_ROI_BWD_EVICT_FIRST");
-    p.evict_first = e ? atoi(e) : 1;
-    const char* e3 = getenv("UNIT_ROI_BWD_SWEEP3");
-    p.sweep3 = e3 ? atoi(e3) : 1;
-  }
+  p.evict_first = switches().bwd_evict_first;
+  p.sweep3 = switches().bwd_sweep3;
   const long long total = (long long)N * C * H * W;  // multiple of 64
   const long long n4 = total / 4 + 16;
   const int zgrid = (int)std::min<long long>((n4 + 255) / 256, (long long)sm_count() * 8);

@@ -278,8 +278,7 @@ static int launch_t(const void* feat, const float* rois, void* out, int N, int C
   p.aligned = aligned;
   p.pair_stride = v2::pair_stride_host(H * W);
   p.units_total = (long long)R * (C / v2::CS);
-  const char* dbg = getenv("UNIT_ROI_DEBUG");
-  p.debug = dbg ? atoi(dbg) : 0;
+  p.debug = switches().roi_debug;
   const size_t smem = v2::smem_total<T>(H * W);
   UNIT_CUDA(cudaFuncSetAttribute(v2::roi_align_fwd_slab2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long grid = p.units_total / 48;  // at least 4 RoIs per warp

@@ -502,8 +502,7 @@ static int launch_band_t(const void* feat, const float* rois, void* out, void* t
   p.aligned = aligned;
   p.pair_stride = 0;
   p.units_total = (long long)R * (C / band::CS);
-  const char* dbg = getenv("UNIT_ROI_DEBUG");
-  p.debug = dbg ? atoi(dbg) : 0;
+  p.debug = switches().roi_debug;
   const size_t smem = band::smem_total<T>(H * W);
   UNIT_CUDA(cudaFuncSetAttribute(band::roi_align_fwd_band<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long grid = p.units_total / 48;  // at least 4 RoIs per warp

@@ -243,6 +243,134 @@ __global__ void __launch_bounds__(TT) similarity_transfer_bwd_kernel(const Trans
   }
 }
 
+
+// Gradient of the fused similarity + transfer w.r.t. the visual logits (roi_heads.py:245-257 is NOT under no_grad in
+// the reference: with a trainable box head the fine-tune loss reaches box_features through softmax -> renormalise ->
+// threshold -> S -> bmm).  One CTA per RoI recomputes the forward pieces (p, u, t, S) and applies the chain rule:
+//   gS_cls[n,b]  = g_scores[novel n] * delta[base b]          gS_bbox[n,b] = sum_j g_bbox[novel n, j] * pd[base b, j]
+//   gt = (gS - <gS, S>) / sum(t)      (normalised heads; gt = gS otherwise)
+//   gv[b] = sum_h wv_h sum_n gt_h[n,b];   thresholded entries pass no gradient;   u = pb / sum(pb);   p = softmax(vl)
+struct TransferBwdVisArgs {
+  unit_transfer_params p;
+  const float* vis_logits;
+  const float* stat[2];
+  const int* base;
+  const int* novel;
+  const float* delta_scores;
+  const float* proposal_deltas;
+  const float* g_scores;
+  const float* g_bbox;
+  float* g_vis;
+};
+
+__global__ void __launch_bounds__(TT) similarity_transfer_bwd_vis_kernel(const TransferBwdVisArgs a) {
+  extern __shared__ float sm[];
+  const int K = a.p.K, B = a.p.B, Nn = a.p.Nn, K1 = K + 1;
+  float* s_p = sm;            // [K1] softmax of the visual logits
+  float* s_u = s_p + K1;      // [B]  renormalised base probabilities (before the threshold)
+  float* s_gv = s_u + B;      // [B]  gradient w.r.t. the thresholded visual similarity
+  __shared__ float s_scal[2];
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = TT / 32;
+  const long long ld_d = a.p.ld_delta_scores ? a.p.ld_delta_scores : K1;
+  const long long ld_p = a.p.ld_proposal_deltas ? a.p.ld_proposal_deltas : 4 * K;
+  const float* vl = a.vis_logits + (long long)r * K1;
+  for (int b = tid; b < B; b += TT) s_gv[b] = 0.f;
+  if (warp == 0) {
+    float m = -INFINITY;
+    for (int k = lane; k < K1; k += 32) m = fmaxf(m, vl[k]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int k = lane; k < K1; k += 32) sum += expf(vl[k] - m);
+    sum = warp_sum(sum);
+    for (int k = lane; k < K1; k += 32) s_p[k] = expf(vl[k] - m) / sum;
+    __syncwarp();
+    float bs = 0.f;
+    for (int b = lane; b < B; b += 32) bs += s_p[a.base[b]];
+    bs = warp_sum(bs);
+    const float den = fmaxf(bs, 1e-9f);
+    for (int b = lane; b < B; b += 32) s_u[b] = s_p[a.base[b]] / den;
+    if (lane == 0) {
+      s_scal[0] = den;
+      s_scal[1] = bs >= 1e-9f ? 1.f : 0.f;  // the clamp is inactive: the renormalisation has a gradient of its own
+    }
+  }
+  __syncthreads();
+  const float wv[2] = {a.p.wv_cls, a.p.wv_bbox};
+  const int nrm[2] = {a.p.norm_cls, a.p.norm_bbox};
+  const float thr = a.p.vis_threshold;
+  for (int h = 0; h < 2; ++h) {
+    if (wv[h] == 0.f) continue;
+    for (int n = warp; n < Nn; n += nwarp) {
+      const float* st = a.stat[h] ? a.stat[h] + (((a.p.static_per_roi >> h) & 1) ? (long long)r * Nn * B : 0) + n * B : nullptr;
+      const int kn = a.novel[n];
+      float g4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (h == 0) {
+        g4[0] = a.g_scores[(long long)r * K1 + kn];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g4[j] = a.g_bbox[(long long)r * 4 * K + 4 * kn + j];
+      }
+      float sum = 0.f, dot = 0.f;
+      for (int b = lane; b < B; b += 32) {
+        const float v = s_u[b] < thr ? 0.f : s_u[b];
+        const float t = (st ? st[b] : 0.f) + wv[h] * v;
+        const int kb = a.base[b];
+        float gs;
+        if (h == 0) {
+          gs = g4[0] * a.delta_scores[r * ld_d + kb];
+        } else {
+          const float* pd = a.proposal_deltas + r * ld_p + 4 * kb;
+          gs = g4[0] * pd[0] + g4[1] * pd[1] + g4[2] * pd[2] + g4[3] * pd[3];
+        }
+        sum += t;
+        dot += gs * t;
+      }
+      sum = warp_sum(sum);
+      dot = warp_sum(dot);
+      const float den = fmaxf(sum, 1e-9f);
+      const float mean = (nrm[h] && sum >= 1e-9f) ? dot / den : 0.f;  // <gS, S>
+      for (int b = lane; b < B; b += 32) {
+        const int kb = a.base[b];
+        float gs;
+        if (h == 0) {
+          gs = g4[0] * a.delta_scores[r * ld_d + kb];
+        } else {
+          const float* pd = a.proposal_deltas + r * ld_p + 4 * kb;
+          gs = g4[0] * pd[0] + g4[1] * pd[1] + g4[2] * pd[2] + g4[3] * pd[3];
+        }
+        const float gt = nrm[h] ? (gs - mean) / den : gs;
+        atomicAdd(&s_gv[b], wv[h] * gt);  // <= Nn adds per entry, shared memory
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const float den = s_scal[0], live = s_scal[1];
+    float dot = 0.f;
+    for (int b = lane; b < B; b += 32) {
+      const float gu = s_u[b] < thr ? 0.f : s_gv[b];
+      s_gv[b] = gu;
+      dot += gu * s_u[b];
+    }
+    dot = warp_sum(dot) * live;
+    // gradient w.r.t. the softmax probabilities: non-zero on base columns only
+    float pdot = 0.f;
+    for (int b = lane; b < B; b += 32) {
+      const float gpb = (s_gv[b] - dot) / den;
+      s_gv[b] = gpb;
+      pdot += gpb * s_p[a.base[b]];
+    }
+    pdot = warp_sum(pdot);
+    __syncwarp();
+    for (int k = lane; k < K1; k += 32) a.g_vis[(long long)r * K1 + k] = -s_p[k] * pdot;
+    __syncwarp();
+    for (int b = lane; b < B; b += 32) {
+      const int kb = a.base[b];
+      a.g_vis[(long long)r * K1 + kb] = s_p[kb] * (s_gv[b] - pdot);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------- mask transfer
 __global__ void mask_transfer_kernel(const float* __restrict__ logits, const float* __restrict__ s_seg, int s_is_2d,
                                      const int* __restrict__ base, const int* __restrict__ class_kind,
@@ -526,6 +654,33 @@ int unit_similarity_transfer_bwd(const unit_transfer_params* p, const float* s_c
   return UNIT_OK;
 }
 
+int unit_similarity_transfer_bwd_vis(const unit_transfer_params* p, const float* vis_logits, const float* static_cls,
+                                     const float* static_bbox, const int* base, const int* novel,
+                                     const float* delta_scores, const float* proposal_deltas, const float* g_scores,
+                                     const float* g_bbox, float* g_vis_logits, unit_stream_t stream) {
+  UNIT_REQUIRE(p, "similarity_transfer_bwd_vis: null params");
+  UNIT_REQUIRE(p->R >= 0 && p->K > 0 && p->B > 0 && p->Nn > 0, "similarity_transfer_bwd_vis: bad shape");
+  if (p->R == 0) return UNIT_OK;
+  UNIT_REQUIRE(vis_logits && base && novel && delta_scores && proposal_deltas && g_scores && g_bbox && g_vis_logits,
+               "similarity_transfer_bwd_vis: null pointer");
+  TransferBwdVisArgs a;
+  a.p = *p;
+  a.vis_logits = vis_logits;
+  a.stat[0] = static_cls;
+  a.stat[1] = static_bbox;
+  a.base = base;
+  a.novel = novel;
+  a.delta_scores = delta_scores;
+  a.proposal_deltas = proposal_deltas;
+  a.g_scores = g_scores;
+  a.g_bbox = g_bbox;
+  a.g_vis = g_vis_logits;
+  const size_t smem = (size_t)((p->K + 1) + 2 * p->B + 8) * sizeof(float);
+  similarity_transfer_bwd_vis_kernel<<<p->R, TT, smem, (cudaStream_t)stream>>>(a);
+  UNIT_CHECK_LAUNCH("similarity_transfer_bwd_vis_kernel");
+  return UNIT_OK;
+}
+
 int unit_mask_transfer(const float* logits, const float* s_seg, int s_is_2d, const int* base, const int* novel,
                        const int* class_kind, const float* x_delta, const int64_t* pred_classes, float* out_logits,
                        float* out_probs, int D, int K, int B, int Nn, int MM, unit_stream_t stream) {
@@ -548,7 +703,7 @@ int unit_mask_paste(const float* masks, const float* boxes, int D, int M, int im
   UNIT_REQUIRE(masks && boxes && out, "mask_paste: null pointer");
   UNIT_REQUIRE((((uintptr_t)boxes) & 15) == 0, "mask_paste: boxes must be 16-byte aligned");
   const long long total = (long long)D * img_h * img_w;
-  if (threshold > 0.f && D <= 65535 && !getenv("UNIT_PASTE_FLAT")) {  // outside value is 0: clear, then visit the box windows only
+  if (threshold > 0.f && D <= 65535 && !switches().paste_flat) {  // outside value is 0: clear, then visit the box windows only
     UNIT_CUDA(cudaMemsetAsync(out, 0, (size_t)total, (cudaStream_t)stream));
     dim3 grid(cdiv(img_h, unit::transfer::WIN_ROWS), D);
     mask_paste_window_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(masks, (const float4*)boxes, M, img_h, img_w,

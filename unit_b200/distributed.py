@@ -31,20 +31,43 @@ class FlatGradBucket:
         dev, dt = self.params[0].device, self.params[0].dtype
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, device=dev, dtype=dt)
+        self._offsets = []
         off = 0
         for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+            self._offsets.append(off)
+            off += p.numel()
+        self.bind()
+
+    def bind(self) -> None:
+        """(Re-)install ``param.grad`` as views of the flat buffer.  ``optimizer.zero_grad()`` /
+        ``Module.zero_grad()`` default to ``set_to_none=True``, which drops the views: backward would then allocate
+        fresh ``.grad`` tensors and the all-reduce would run on an orphaned buffer.  Call ``bucket.zero_()`` instead
+        of ``zero_grad()`` (or ``zero_grad(set_to_none=False)``); ``zero_`` re-binds, ``all_reduce_mean`` verifies."""
+        for p, off in zip(self.params, self._offsets):
+            g = p.grad
+            if g is None or g.data_ptr() != self.flat.data_ptr() + off * self.flat.element_size():
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+
+    def check_bound(self) -> None:
+        es = self.flat.element_size()
+        for p, off in zip(self.params, self._offsets):
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * es:
+                raise RuntimeError(
+                    "FlatGradBucket: a parameter's .grad is no longer a view of the flat bucket (zero_grad("
+                    "set_to_none=True) or an external assignment replaced it); gradients would not be all-reduced. "
+                    "Use bucket.zero_() / zero_grad(set_to_none=False), or call bucket.bind() before backward.")
 
     @property
     def nbytes(self) -> int:
         return self.flat.numel() * self.flat.element_size()
 
     def zero_(self) -> None:
+        """Clear the bucket and make sure every ``param.grad`` (still) aliases it."""
+        self.bind()
         self.flat.zero_()
 
     def all_reduce_mean(self, async_op: bool = False):
+        self.check_bound()
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return None
         self._avg = dist.get_backend() == "nccl"  # NCCL averages inside the collective; gloo needs sum + divide

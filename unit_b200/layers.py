@@ -33,10 +33,19 @@ def _adjacent_rows(tensors: List[torch.Tensor]) -> Optional[torch.Tensor]:
             return None
         nxt += t.numel()
         rows += t.shape[0]
-    return first.as_strided((rows,) + tuple(rest), first.stride(), first.storage_offset())
+    # strides computed from the shape: ``is_contiguous`` ignores the stride of a size-1 dim, so a 1-row slice of a
+    # wider parent may carry a row stride that is wrong for the combined view
+    strides, acc = [], 1
+    for d in reversed((rows,) + tuple(rest)):
+        strides.append(acc)
+        acc *= max(int(d), 1)
+    return first.as_strided((rows,) + tuple(rest), tuple(reversed(strides)), first.storage_offset())
 
 
 def cat(tensors: List[torch.Tensor], dim: int = 0) -> torch.Tensor:
+    """``torch.cat`` for kernel INPUTS: the result may alias the sources (a single tensor is returned as is, adjacent
+    row blocks of one buffer come back as one view), so callers must treat it as read-only.  Everything in this
+    package that mutates boxes in place (Boxes.clip / scale) works on tensors it owns, never on this result."""
     if len(tensors) == 1:
         return tensors[0]
     if dim == 0:

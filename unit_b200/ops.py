@@ -28,15 +28,22 @@ def _stream() -> ctypes.c_void_p:
 
 
 def _need_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    """All tensors on ONE CUDA device, and that device must be the current one: the library launches on the current
+    device's current stream (one process per GPU), so a tensor of another device would silently run elsewhere."""
     dev = None
     for t in tensors:
         if t is None:
             continue
         if not t.is_cuda:
             raise RuntimeError("unit_b200 ops run on CUDA tensors only (there is no CPU path)")
+        if dev is not None and t.device != dev:
+            raise RuntimeError(f"unit_b200 op called with tensors on {dev} and {t.device}")
         dev = t.device
     if dev is None:
         raise RuntimeError("unit_b200 op called without tensors")
+    if dev.index is not None and dev.index != torch.cuda.current_device():
+        raise RuntimeError(f"unit_b200 op called with tensors on {dev} while the current device is "
+                           f"cuda:{torch.cuda.current_device()}; wrap the call in torch.cuda.device({dev.index})")
     return dev
 
 
@@ -592,11 +599,36 @@ def similarity_transfer_backward(spec: TransferSpec, s_cls, s_bbox, g_scores, g_
     return g_delta, g_pd
 
 
-class _TransferFn(torch.autograd.Function):
-    """Autograd of the fused transfer w.r.t. (delta_scores, proposal_deltas, ft_scores, ft_deltas).
+def similarity_transfer_backward_vis(spec: TransferSpec, vis_logits, delta_scores, proposal_deltas, g_scores, g_bbox):
+    """d loss / d vis_logits of the fused similarity + transfer (recomputes S in the kernel; nothing is saved)."""
+    dev = _need_cuda(vis_logits, g_scores, g_bbox)
+    R = g_scores.shape[0]
+    g_vis = torch.empty((R, spec.K + 1), dtype=_F32, device=dev)
+    if R:
+        def rows(t):
+            if t.dtype == _F32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+                return t, t.stride(0)
+            return _c(t, _F32), 0
 
-    The similarity is treated as a constant (it is built from frozen weights in every shipped fine-tune YAML,
-    configs/VOC/FT/*/...-ft.yaml:6-9); a vis_logits tensor that requires grad is rejected.
+        (delta_scores, ld_d), (proposal_deltas, ld_p) = rows(delta_scores), rows(proposal_deltas)
+        p = spec.params(R, True, False)
+        p.ld_delta_scores, p.ld_proposal_deltas = ld_d, ld_p
+        check(lib().unit_similarity_transfer_bwd_vis(ctypes.byref(p), _ptr(_c(vis_logits, _F32)),
+                                                     _ptr(spec.static.get("cls")), _ptr(spec.static.get("bbox")),
+                                                     _ptr(spec.base_i32), _ptr(spec.novel_i32), _ptr(delta_scores),
+                                                     _ptr(proposal_deltas), _ptr(_c(g_scores, _F32)),
+                                                     _ptr(_c(g_bbox, _F32)), _ptr(g_vis), _stream()),
+              "unit_similarity_transfer_bwd_vis")
+    return g_vis
+
+
+class _TransferFn(torch.autograd.Function):
+    """Autograd of the fused transfer w.r.t. (vis_logits, delta_scores, proposal_deltas, ft_scores, ft_deltas).
+
+    The gradient w.r.t. ``vis_logits`` is what the reference gets from running get_similarity_matrices
+    (roi_heads.py:245-257) with autograd on: with a trainable box head the fine-tune loss reaches box_features
+    through the visual similarity.  The class-level terms (lingual, TopK ...) are built from frozen tensors
+    (embeddings; ``.clone().detach()`` weights, roi_heads.py:275,286,297) and carry no gradient in the reference either.
     """
 
     @staticmethod
@@ -604,6 +636,9 @@ class _TransferFn(torch.autograd.Function):
                 novel_neg_inf, detach_transfer, ft_packed=None):
         need_grad = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         ctx.need_delta_grad = need_grad
+        # detach_transfer (fast_rcnn.py:566,575) cuts the transferred part out of the graph: no similarity gradient
+        ctx.need_vis_grad = bool(ctx.needs_input_grad[1] and do_transfer and vis_logits is not None
+                                 and not detach_transfer)
         ctx.ft_is_packed = ft_packed is not None
         if ft_packed is not None:  # [R, (K+1) + 4K]: both fine-tune blocks of one GEMM output, one gradient tensor
             K1 = delta_scores.shape[1]
@@ -613,7 +648,11 @@ class _TransferFn(torch.autograd.Function):
                                                                  weak_scores, ft_scores, ft_deltas, do_transfer,
                                                                  novel_neg_inf, want)
         ctx.spec, ctx.do_transfer, ctx.detach, ctx.neg_inf = spec, do_transfer, detach_transfer, novel_neg_inf
-        ctx.save_for_backward(*(t for t in (sims["cls"], sims["bbox"]) if t is not None))
+        saved = [t for t in (sims["cls"], sims["bbox"]) if t is not None]
+        ctx.n_sims = len(saved)
+        if ctx.need_vis_grad:
+            saved += [vis_logits, delta_scores, proposal_deltas]
+        ctx.save_for_backward(*saved)
         ctx.has_ft = (ft_scores is not None, ft_deltas is not None)
         return out_scores, out_bbox
 
@@ -628,24 +667,30 @@ class _TransferFn(torch.autograd.Function):
         if not ctx.need_delta_grad:  # frozen delta layers (fine-tuning): nothing flows through the transfer
             g_delta = g_pd = None
         elif ctx.do_transfer:
-            s_cls, s_bbox = (saved[0], saved[1]) if len(saved) == 2 else (None, None)
+            s_cls, s_bbox = (saved[0], saved[1]) if ctx.n_sims == 2 else (None, None)
             g_delta, g_pd = similarity_transfer_backward(ctx.spec, s_cls, s_bbox, g_scores, g_bbox,
                                                          detach_transfer=ctx.detach or s_cls is None)
         else:
             g_delta, g_pd = g_scores, g_bbox
+        g_vis = None
+        if ctx.need_vis_grad:
+            vis_logits, delta_scores, proposal_deltas = saved[ctx.n_sims:]
+            g_vis = similarity_transfer_backward_vis(ctx.spec, vis_logits, delta_scores, proposal_deltas, g_scores,
+                                                     g_bbox)
         if ctx.ft_is_packed:
-            return (None, None, g_delta, g_pd, None, None, None, None, None, None,
+            return (None, g_vis, g_delta, g_pd, None, None, None, None, None, None,
                     torch.cat([g_scores, g_bbox], 1))
-        return (None, None, g_delta, g_pd, None, g_scores if ctx.has_ft[0] else None,
+        return (None, g_vis, g_delta, g_pd, None, g_scores if ctx.has_ft[0] else None,
                 g_bbox if ctx.has_ft[1] else None, None, None, None, None)
 
 
 def similarity_transfer(spec: TransferSpec, vis_logits, delta_scores, proposal_deltas, weak_scores=None,
                         ft_scores=None, ft_deltas=None, do_transfer=True, novel_neg_inf=False,
                         detach_transfer=False, ft_packed=None):
-    if vis_logits is not None and vis_logits.requires_grad:
-        raise RuntimeError("similarity_transfer: gradients through the visual similarity are not implemented "
-                           "(it is computed from frozen weights in every shipped fine-tune config)")
+    if vis_logits is not None and vis_logits.requires_grad and do_transfer and not detach_transfer:
+        if spec.static_per_roi or getattr(spec, "wk", None):
+            raise NotImplementedError("similarity_transfer: gradients through a per-RoI static similarity block "
+                                      "('VisualK-k' terms) are not implemented; only the 'visual' term is")
     return _TransferFn.apply(spec, vis_logits, delta_scores, proposal_deltas, weak_scores, ft_scores, ft_deltas,
                              bool(do_transfer), bool(novel_neg_inf), bool(detach_transfer), ft_packed)
 

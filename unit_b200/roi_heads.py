@@ -341,10 +341,15 @@ class WSROIHead(StandardROIHeads):
         vis_logits = None
         if self.compute_similarity["visual"] or spec.wk:
             feats = box_features.mean(dim=[2, 3]) if box_features.dim() > 2 else box_features
-            with torch.no_grad():
+            # The reference builds the similarity with autograd on (roi_heads.py:245-257, 618): with a trainable box
+            # head (COCO-*-ft.yaml, VOC 10-shot split 2/3) the loss reaches box_features through it.  Frozen features
+            # (the usual fine-tune setting, and inference) skip the graph.
+            track = torch.is_grad_enabled() and feats.requires_grad
+            with torch.set_grad_enabled(track):
                 vis_logits = self.box_predictor.weak_detector_head.mean_logits(feats)
+            with torch.no_grad():
                 if spec.wk:
-                    spec = self._visualk_spec(spec, vis_logits)
+                    spec = self._visualk_spec(spec, vis_logits.detach())
         sim = FusedSimilarity(spec, vis_logits, tuple(self.terms.keys()))
         if return_similarity:
             raw, _ = ops.lingual_similarity(self.box_predictor.embeddings.weight, self._coco_indexer_tensor,
