@@ -367,9 +367,11 @@ def cpu_workload(rank=0):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port: torchvision CPU kernels +
-    restated Detectron2 / UniT glue) on all host cores.  Each step runs label/sample + transfer on the full
-    workload and ROIAlign fwd+bwd on a bounded sample of RoIs, scaled to the full 512 RoIs/image."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: torchvision's compiled CPU
+    ROIAlign kernels + the restated Detectron2 / UniT glue) on all host cores.  Every TIMED step is the FULL workload
+    -- label/sample, ROIAlign forward + backward over all 2 x 512 RoIs, transfer + loss + backward -- measured by wall
+    clock; nothing is sampled or scaled.  Warm-up steps run the same code on 32 RoIs per image (they are untimed and
+    only page the libraries in), so that K = 20 timed steps (~9 s each on 16 cores) finish in about three minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -377,21 +379,23 @@ def run_reference(args):
     torch.set_num_threads(cores)
     w, meta, x, xw, gp = cpu_workload()
     sets = [make_inputs(2000 + s) for s in range(2)]
-    roi_sample = 32
     gen = _seeded(1000)
     for i in range(max(args.warmup, 1)):
-        cpu_reference_step(sets[i % 2], w, meta, gen, x, xw, gp, roi_sample)
-    est = []
+        cpu_reference_step(sets[i % 2], w, meta, gen, x, xw, gp, 32)
+    per_step, parts = [], [0.0, 0.0, 0.0]
     t_wall = time.perf_counter()
     for i in range(args.steps):
-        _, tl, tr, tp, _, _ = cpu_reference_step(sets[i % 2], w, meta, gen, x, xw, gp, roi_sample)
-        est.append(tl + tp + tr * (BATCH / roi_sample))
+        t0 = time.perf_counter()
+        _, tl, tr, tp, _, _ = cpu_reference_step(sets[i % 2], w, meta, gen, x, xw, gp, None)
+        per_step.append(time.perf_counter() - t0)
+        parts = [parts[0] + tl, parts[1] + tr, parts[2] + tp]
     t_wall = time.perf_counter() - t_wall
-    ms = 1000.0 * sum(est) / len(est)
+    ms = 1000.0 * t_wall / args.steps
     value = N_IMG / (ms / 1000.0)
-    sample = (f"per step: label+sample and transfer+loss+backward on the full 2x512-RoI workload, ROIAlign fwd+bwd "
-              f"on {roi_sample} of 512 RoIs/image and scaled x{BATCH // roi_sample}; wall {t_wall:.1f}s for "
-              f"{args.steps} steps")
+    sample = (f"every timed step is the full workload (2 images x 512 RoIs, C=1024): wall {t_wall:.1f}s for {args.steps} "
+              f"steps; mean per step: label+sample {1e3 * parts[0] / args.steps:.1f} ms, ROIAlign fwd+bwd "
+              f"{1e3 * parts[1] / args.steps:.0f} ms, transfer+loss+backward {1e3 * parts[2] / args.steps:.1f} ms; "
+              f"min/max step {min(per_step):.2f}/{max(per_step):.2f} s; warm-up steps use 32 RoIs/image (untimed)")
     line = {
         "impl": "reference", "metric": "RoI-stage images/sec (VOC R101-C4 FT train step)", "value": value,
         "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -416,6 +420,104 @@ def workload_config(dtype):
         "parallelism": "images sharded across GPUs, no data-path collective; one NCCL all-reduce of the flat "
                        "0.83 MB cls_score_ft/bbox_pred_ft gradient bucket per step",
     }
+
+
+
+# ------------------------------------------------------------------------------------------------- comparison arms
+def _tv_style_inference_gpu(boxes, scores, n_img, per_img, K, score_thresh, nms_thresh, topk):
+    """What a stock Detectron2 does on the GPU for fast_rcnn_inference: a per-image Python loop of
+    mask -> nonzero -> torchvision.ops.batched_nms -> top-k (comparison arm only, library kernels)."""
+    import torchvision
+
+    out = []
+    for i in range(n_img):
+        b = boxes[i * per_img:(i + 1) * per_img].view(per_img, K, 4)
+        sc = scores[i * per_img:(i + 1) * per_img, :K]
+        mask = sc > score_thresh
+        idx = mask.nonzero()
+        bb, ss = b[mask], sc[mask]
+        keep = torchvision.ops.batched_nms(bb, ss, idx[:, 1], nms_thresh)[:topk]
+        out.append((bb[keep], ss[keep], idx[keep]))
+    return out
+
+
+def aux_comparison(device, wl, flush, ops):
+    """aux.torchvision_cuda + aux.nms_batch_sweep: the kernels the reference actually runs on a GPU (torchvision's CUDA
+    roi_align / batched_nms, the bars SURVEY.md section 2a names) timed next to ours on the same box, and the
+    SURVEY 8(d) honest-caveat sweeps for NMS.  Library kernels appear ONLY here, as the thing compared against."""
+    import torchvision
+
+    g = _seeded(909)
+    res = {}
+    # ---- ROIAlign forward / backward at the bench shapes
+    feats = wl.dev_sets[0][0].float()
+    rois = torch.cat([torch.cat([torch.full((BATCH, 1), float(i)), _boxes(BATCH, IMG_HW[0], IMG_HW[1], g)], 1)
+                      for i in range(N_IMG)]).to(device)
+    gout = wl.grad_pooled.float()
+    fwd_tv = lambda: torchvision.ops.roi_align(feats, rois, 14, 1 / 16, 0, True)
+    bwd_tv = lambda: torch.ops.torchvision._roi_align_backward(gout, rois, 1 / 16, 14, 14, N_IMG, C, H, W, 0, True)
+    fwd = lambda: ops.roi_align_forward(feats, rois, (14, 14), 1 / 16, 0, True, True)
+    bwd = lambda: ops.roi_align_backward(gout, rois, feats.shape, 1 / 16, 0, True, True)
+    for f in (fwd_tv, bwd_tv, fwd, bwd):
+        f()
+    res["roi_align_2x512_c1024_f32"] = {
+        "torchvision_fwd_ms": time_kernel(fwd_tv, 5, flush), "ours_fwd_ms": time_kernel(fwd, 10, flush),
+        "torchvision_bwd_ms": time_kernel(bwd_tv, 5, flush), "ours_bwd_ms": time_kernel(bwd, 10, flush),
+        "what": "torch.ops.torchvision.roi_align / _roi_align_backward (CUDA) vs unit_roi_align_fwd / _bwd, "
+                "[2,1024,50,84] fp32, 2 x 512 RoIs, CUDA events, L2 flushed"}
+    # ---- batched NMS, one call, Nc candidates over 80 classes (SURVEY 8d NMS-boundary micro-bench)
+    sweep = {}
+    for nc in (1000, 4000, 20000, 80000):
+        bx = _boxes(nc, IMG_HW[0], IMG_HW[1], g).to(device)
+        sc = (0.05 + 0.95 * torch.rand(nc, generator=g) + torch.arange(nc) * 2.0 ** -24).to(device)  # tie-free
+        ids = torch.randint(0, 80, (nc,), generator=g).to(device)
+        tv = lambda: torchvision.ops.batched_nms(bx, sc, ids, 0.5)
+        ours = lambda: ops.batched_nms(bx, sc, ids, 0.5)
+        k_tv, k_ours = tv(), ours()
+        t_tv, t_ours = time_kernel(tv, 5, flush), time_kernel(ours, 5, flush)
+        alg = 36 * nc
+        sweep[str(nc)] = {"torchvision_ms": t_tv, "ours_ms": t_ours, "keep_equal": bool(torch.equal(k_tv, k_ours)),
+                          "kept": int(k_ours.numel()), "algorithmic_bytes": alg,
+                          "ours_GBps": alg / (t_ours * 1e-3) / 1e9}
+    res["batched_nms_one_call"] = {
+        "by_candidates": sweep,
+        "what": "torchvision.ops.batched_nms (CUDA) vs unit_batched_nms, boxes as the proposals, scores U(0.05,1) "
+                "tie-free, 80 classes, IoU 0.5; both end with the same host read of the keep count; algorithmic bytes "
+                "= 36 B per candidate (SURVEY 8d) -- KB to a few MB, i.e. launch/latency-bound, not an HBM roofline"}
+    # ---- decode + filter + class-wise NMS + top-100 for a BATCH of images in one call (SURVEY 8d honest caveat)
+    batch = {}
+    K, per = 80, 1000
+    for n_img in (1, 2, 16, 64):
+        R = n_img * per
+        scores = torch.softmax(4.0 * torch.randn(R, K + 1, generator=g), -1).to(device)
+        deltas = (0.2 * torch.randn(R, 4 * K, generator=g)).to(device)
+        pb = torch.cat([_boxes(per, IMG_HW[0], IMG_HW[1], g) for _ in range(n_img)]).to(device)
+        off = ops.offsets_from_counts([per] * n_img, device)
+        hw = torch.tensor([[float(IMG_HW[0]), float(IMG_HW[1])]] * n_img, device=device)
+
+        def ours():
+            _, boxes = ops.softmax_decode(None, deltas, pb, want_probs=False)
+            return ops.detect(boxes, scores, off, hw, 0.05, 0.5, 100)
+
+        def stock():
+            _, boxes = ops.softmax_decode(None, deltas, pb, want_probs=False)  # same decoded boxes for both arms
+            return _tv_style_inference_gpu(boxes, scores, n_img, per, K, 0.05, 0.5, 100)
+
+        out = ours()
+        stock()
+        n_cand = int(out[5][4].sum().item())
+        t_ours, t_stock = time_kernel(ours, 5, flush), time_kernel(stock, 3, flush)
+        alg = R * (K + 1) * 4 + R * 4 * K * 4 + R * 16 + 36 * n_cand + 36 * n_cand
+        batch[str(n_img)] = {"ours_ms": t_ours, "torchvision_loop_ms": t_stock, "candidates": n_cand,
+                             "algorithmic_bytes": alg, "ours_GBps": alg / (t_ours * 1e-3) / 1e9,
+                             "images_per_s": n_img / (t_ours * 1e-3)}
+    res["decode_filter_nms_by_batch"] = {
+        "by_images": batch,
+        "what": "softmax_decode + detect (filter, grouped class-wise NMS, top-100) for n images x 1000 proposals x 80 "
+                "classes in ONE call sequence vs the stock per-image loop (mask, nonzero, torchvision batched_nms, "
+                "top-k) on the same decoded boxes; CUDA events, L2 flushed; bytes per SURVEY 8d (scores + deltas + "
+                "proposals read, 36 B per candidate written and re-read)"}
+    return res
 
 
 # ------------------------------------------------------------------------------------------------- main arm
@@ -629,6 +731,7 @@ def run_ours(args):
                 "what": "MIL image loss + 3 x (OICR pseudo-labelling + weighted CE) with gradients, 2 images x 2000 "
                         "proposals, K=20: 15 launches, eager, CUDA events"}
             wl.head.train()
+            aux["torchvision_cuda"] = aux_comparison(device, wl, flush, ops)
 
     # CPU baseline on the box's host cores (rank 0, N = 1 only): the oracle port on a bounded sample
     cpu_baseline = None
@@ -639,17 +742,15 @@ def run_ours(args):
         w, meta, x, xw, gp = cpu_workload()
         hs = make_inputs(2000)
         gen = _seeded(1000)
-        roi_sample = 64
-        cpu_reference_step(hs, w, meta, gen, x, xw, gp, 8)  # warm-up
+        cpu_reference_step(hs, w, meta, gen, x, xw, gp, 8)  # warm-up (8 RoIs/image: pages the libraries in)
         t0 = time.perf_counter()
-        _, tl, tr, tp, _, _ = cpu_reference_step(hs, w, meta, gen, x, xw, gp, roi_sample)
+        _, tl, tr, tp, _, _ = cpu_reference_step(hs, w, meta, gen, x, xw, gp, None)
         wall = time.perf_counter() - t0
-        est = tl + tp + tr * (BATCH / roi_sample)
         cpu_baseline = {
-            "value": N_IMG / est, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"one step: label+sample and transfer+loss+backward on the full 2x512-RoI workload, ROIAlign "
-                      f"fwd+bwd on {roi_sample} of 512 RoIs/image scaled x{BATCH // roi_sample} "
-                      f"(measured {wall:.1f}s, estimated full step {est:.1f}s)",
+            "value": N_IMG / wall, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"ONE full step measured by wall clock, nothing scaled ({wall:.1f}s: label+sample {tl * 1e3:.1f} ms, "
+                      f"ROIAlign fwd+bwd over all 2x512 RoIs {tr:.2f}s, transfer+loss+backward {tp * 1e3:.1f} ms); "
+                      f"`--impl reference` times {{steps}} such steps",
         }
 
     if rank == 0:
@@ -677,6 +778,152 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------- inference arm
+def run_infer(args):
+    """--mode infer: the inference side of the stage, weak scaling over the GPUs of one box, ending in the gather of
+    the detections the reference's evaluator performs (data/evaluators.py:159 -> comm.gather): every rank runs
+    RoIStage.infer_graphed on its own 2 images x 512 proposals (BASELINE.json configs[0] shapes, on the GPU), then
+    distributed.gather_detections all-gathers the padded <= 100 detections per image over NCCL and the counts are
+    read on the host.  Same JSON contract as the training arm."""
+    import torch.distributed as dist
+
+    from unit_b200 import _lib, distributed as udist
+    from unit_b200.stage import RoIStage
+    from unit_b200.structures import Boxes, Instances
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --mode infer needs a CUDA device")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    P_INF = 512
+    head = build_head(device).eval()
+    g = _seeded(77 + rank)
+    x = torch.relu(torch.randn(N_IMG * P_INF, FEAT_DIM, generator=g)).to(device)
+    xw = torch.relu(torch.randn(N_IMG * P_INF, FEAT_DIM, generator=g)).to(device)
+    stage = RoIStage(head, lambda pooled: (x, xw))
+    topk = head.box_predictor.test_topk_per_image
+    host = []
+    for s_ in range(N_SETS):
+        f, pr, _, _ = make_inputs(3000 + 10 * rank + s_)
+        host.append((f.pin_memory(), [p[:P_INF].contiguous().pin_memory() for p in pr]))
+    dev_sets = []
+    for f, pr in host:
+        dev_sets.append((f.to(device), [Instances(IMG_HW, proposal_boxes=Boxes(p.to(device)),
+                                                  objectness_logits=torch.zeros(P_INF, device=device)) for p in pr]))
+    copy_stream = torch.cuda.Stream(device=device)
+    copied = [torch.cuda.Event() for _ in range(N_SETS)]
+    freed = [torch.cuda.Event() for _ in range(N_SETS)]
+    for e in freed:
+        e.record(torch.cuda.current_stream(device))
+    counts_pinned = torch.zeros(world * N_IMG, dtype=torch.int32).pin_memory()
+    n_det = [0]
+
+    def gather(dets):
+        db, ds, dc, _, cnt = dets
+        _, _, _, n = udist.gather_detections(db, ds, dc, cnt, topk)
+        counts_pinned.copy_(torch.cat(n), non_blocking=False)  # the host read the evaluator needs
+        n_det[0] = int(counts_pinned.sum())
+
+    def step(i):
+        with torch.no_grad():
+            dets = stage.infer_graphed(*dev_sets[i % N_SETS], padded=True)
+            gather(dets)
+
+    issued = [-1]
+
+    def issue(j):
+        k = j % N_SETS
+        copy_stream.wait_event(freed[k])
+        with torch.cuda.stream(copy_stream):
+            f, pr = host[k]
+            dev_sets[k][0].copy_(f, non_blocking=True)
+            for inst, src in zip(dev_sets[k][1], pr):
+                inst.proposal_boxes.tensor.copy_(src, non_blocking=True)
+            copied[k].record(copy_stream)
+        issued[0] = j
+
+    e2e_n = [0]
+
+    def step_e2e(_i):
+        j = e2e_n[0]
+        e2e_n[0] += 1
+        main = torch.cuda.current_stream(device)
+        while issued[0] < j + 2:
+            issue(issued[0] + 1)
+        k = j % N_SETS
+        main.wait_event(copied[k])
+        with torch.no_grad():
+            dets = stage.infer_graphed(*dev_sets[k], padded=True)
+        freed[k].record(main)
+        gather(dets)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            fn(i)
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(N_SETS + args.warmup):
+        step(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    total_ms = timed(step, args.steps)
+    for i in range(3):
+        step_e2e(i)
+    e2e_ms = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    # kernels inside the replayed graph: count them once with an eager call
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        stage.infer(*dev_sets[0])
+    per_call = _lib.launch_count() - n0
+    if rank == 0:
+        ms_step = total_ms / args.steps
+        h2d = int(host[0][0].numel() * 4 + sum(p.numel() * 4 for p in host[0][1]))
+        line = {
+            "metric": "RoI-stage inference images/sec (VOC R101-C4, 512 proposals/img)",
+            "value": world * N_IMG / (ms_step / 1e3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "mode": "infer",
+            "config": {"workload": "BASELINE.json configs[0] shapes on the GPU: VOC-RCNN-101-C4-split1 RoI-stage inference, 2 "
+                                   "synthetic 800x1333 images per GPU, 512 proposals/img, 15 base + 5 novel classes: ROIAlign "
+                                   "fwd -> transfer -> softmax+decode -> filter -> class-wise NMS -> top-100, then the "
+                                   "all-gather of the padded detections over NCCL and the host read of their counts",
+                       "box_head": "res5 excluded (out of scope): fixed synthetic [1024,2048] box features",
+                       "l2": f"inputs rotate over {N_SETS} sets (137 MB of features + 822 MB ROIAlign output per call)",
+                       "parallelism": "images sharded across GPUs; the only collective is the final all-gather of "
+                                      "detections (reference: data/evaluators.py:159)"},
+            "e2e": {"value": world * N_IMG / (e2e_ms / args.steps / 1e3), "unit": "images/s",
+                    "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(world * N_IMG * 4)},
+            "gpu_launches": int(per_call * args.steps), "detections_last_step": n_det[0], "clocks": clocks,
+            "gathered_bytes_per_rank": int(N_IMG * (6 * topk + 1) * 4),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -684,6 +931,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--dtype", choices=["f32", "bf16"], default="f32")
+    ap.add_argument("--mode", choices=["train", "infer"], default="train",
+                    help="train: the fine-tune step (BASELINE metric, default); infer: inference + detection gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to its GPU's NUMA-local CPUs")
@@ -695,6 +944,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "infer":
+        run_infer(args)
     else:
         run_ours(args)
 

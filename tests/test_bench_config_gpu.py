@@ -102,7 +102,8 @@ def test_train_step_bench_config_tf32_vs_oracle(bench):
     head.sampling_generator = seeded(1000)
     bucket = FlatGradBucket([p for p in head.parameters() if p.requires_grad])
     w, meta, x, xw, gp = bench.cpu_workload()
-    stage = RoIStage(head, lambda pooled: (x.to(dev), xw.to(dev)), bucket)
+    x_dev, xw_dev = x.to(dev), xw.to(dev)
+    stage = RoIStage(head, lambda pooled: (x_dev, xw_dev), bucket)
     host = bench.make_inputs(2000)
     feats, props, gts, gcls = host
     d_props = [Instances(bench.IMG_HW, proposal_boxes=Boxes(p.to(dev)), objectness_logits=torch.zeros(len(p), device=dev))
@@ -135,8 +136,8 @@ def test_train_step_bench_config_tf32_vs_oracle(bench):
     pooled = ops.roi_align_forward(feats.to(dev), ref["rois"].to(dev), (14, 14), 1 / 16, 0, True, True)
     assert_close_rms(pooled.cpu(), ref_pooled, 1e-5, "pooled at bench shapes")
     with torch.no_grad():
-        sim = head.get_similarity_matrices(x.to(dev))
-        (scores, bbox), _ = pred(x.to(dev), supervised_branch_x_weak=xw.to(dev), novel_classes=head._novel_classes_tensor,
+        sim = head.get_similarity_matrices(x_dev)
+        (scores, bbox), _ = pred(x_dev, supervised_branch_x_weak=xw_dev, novel_classes=head._novel_classes_tensor,
                                  base_classes=head._base_classes_tensor, similarity=sim)
     assert _rel(scores, ref["scores"]) <= 1e-2
     assert _rel(bbox, ref["bbox"]) <= 1e-2
@@ -161,7 +162,8 @@ def test_inference_bench_config_tf32_vs_oracle(bench, graphed):
     dev = torch.device("cuda")
     head = bench.build_head(dev).eval()
     w, meta, x, xw, _ = bench.cpu_workload()
-    stage = RoIStage(head, lambda pooled: (x.to(dev), xw.to(dev)))
+    x_dev, xw_dev = x.to(dev), xw.to(dev)
+    stage = RoIStage(head, lambda pooled: (x_dev, xw_dev))
     feats, props, _, _ = bench.make_inputs(3000)
     boxes = [p[:512] for p in props]
     d_props = [Instances(bench.IMG_HW, proposal_boxes=Boxes(b.to(dev)), objectness_logits=torch.zeros(512, device=dev))

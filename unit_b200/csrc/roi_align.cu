@@ -160,8 +160,7 @@ int unit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, in
   UNIT_REQUIRE(feat && rois && out, "roi_align_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (rois_sorted && PH == 14 && PW == 14 && N > 0 && fwd_band_fits(C, H, W, dtype) &&
-      (dtype == UNIT_F32 || switches().fwd_band_bf16) &&
-      !switches().fwd_v3) {  // bf16 I/O: the pair-interleaved kernel below loads its slab faster
+      !switches().fwd_v3) {  // fp32 and bf16 I/O take the same band-gather kernel (the slab is fp32 either way)
     const size_t need = offsets_bytes(N) + fwd_band_workspace_bytes(R);
     if (!workspace || workspace_bytes < need) {
       set_error("roi_align_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);

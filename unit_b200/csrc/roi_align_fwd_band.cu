@@ -9,14 +9,17 @@
 //   out[ph][pw] = sum_y Wy[ph][y] * ( sum_j wb[pw][j] * F[y][bx[pw] + j] )
 // where wb[pw][.] are bin pw's x-samples pre-summed into a dense band of nb <= 8 columns starting at bx[pw].
 //   * a tiny pre-kernel builds every RoI's tables ONCE (the main kernel would otherwise rebuild them for each of
-//     the C/8 slabs): x-bands, and the y-samples as (hy, ly) with "row advances" / "bin ends" flags (same fp32
-//     operation order as torchvision for every coordinate, so floor / validity decisions are the reference's);
+//     the C/8 slabs): the x-bands, and the y-samples as (hy, ly) with an "this sample's lower tap row is one past the
+//     previous sample's" flag (same fp32 operation order as torchvision for every coordinate, so floor / validity
+//     decisions are the reference's);
 //   * lane (pw, half) owns output COLUMN pw of channel quad `half`: its band lives in registers, so one footprint row
-//     costs nb x (LDS.128 + 2 FFMA2) for four channels, and the row walk -- identical for all lanes, so every branch
-//     is warp-uniform -- combines consecutive row sums h(y), h(y+1) with the y-samples; a finished bin goes to the
-//     warp's staging block;
-//   * tables arrive by TMA bulk load (mbarrier) and are consumed into registers at once (y-samples spread over the
-//     lanes, read back by shuffle), so the single table buffer is refilled for the NEXT RoI while this one computes;
+//     costs nb x (LDS.128 + 2 FFMA2) for four channels;
+//   * the walk is SAMPLE-major: for every bin ph, for every y-sample of the bin: one broadcast LDS.64 of the sample's
+//     (hy, ly); if its row advanced, the two live row sums shift (hc <- hn) and the next row sum is formed from pixels
+//     that were requested one row earlier; then acc += hy * hc + ly * hn.  One accumulator set is live (a bin is
+//     finished before the next starts), there are no shuffles, and every branch is warp-uniform;
+//   * tables arrive by TMA bulk load (mbarrier): the x-part is consumed into registers at once, the y-part is double
+//     buffered, so the NEXT RoI's tables load while this one computes;
 //   * the [8 ch][14][14] block -- 6272 contiguous bytes of the NCHW output -- leaves as one TMA bulk store.
 // Every feature byte is read from HBM/L2 once per slab, every output byte is written once, fully coalesced.
 #include "roi_slab.cuh"
@@ -35,26 +38,37 @@ constexpr int NQ = CS / 4;   // channel quads per slab
 constexpr int NW = UNIT_FWD_NW;
 constexpr int NT = NW * 32;
 constexpr int MAXB = 8;      // band columns per bin: sampling grid <= 7 with unit sample steps
-constexpr int MAXGY = 8;
+constexpr int MAXGY = 4;     // y-samples per bin with tables: RoI height <= 56 feature rows (896 px at 1/16)
 constexpr int MAXSY = P * MAXGY;
-constexpr uint32_t F_ADV = 1u, F_END = 2u;  // flags in the two mantissa LSBs of hy (<= 3 ulp on that weight)
+constexpr uint32_t F_ADV = 1u;  // flag in the mantissa LSB of hy (<= 1 ulp on that weight)
 
-struct __align__(16) RoiTab {
-  int mode, gw, gh, nb;  // mode 0: zero output, 1: tables, 2: direct evaluation
-  int y0, nrows, nsy, pad0;
+struct __align__(16) RoiTabX {
+  int mode, nb, y0, gh;  // mode 0: zero output, 1: tables, 2: direct evaluation
+  int gw, nrows, pad0, pad1;
   float inv_count, start_w, start_h, bin_w, bin_h, padf[3];
   int bx[16];            // first column of bin pw's band
   float wb[MAXB][16];    // wb[j][pw]: weight of column bx[pw] + j, already divided by the sample count
-  float2 yt[MAXSY];      // y-sample s: (hy | flags, ly); lower tap row advances by 0 or 1 between samples
+  // lane -> (pw | half << 4 | shadow << 7): which output column / channel quad a lane owns for THIS RoI.  An LDS.128
+  // is served in four phases of 8 lanes; the pre-kernel places the 28 (pw, half) items so that the 8 pixels of a
+  // phase fall into different 16-byte bank groups wherever the RoI's column stride allows it.
+  unsigned char lmap[32];
 };
-static_assert(sizeof(RoiTab) == 1536, "RoiTab layout");
+struct __align__(16) RoiTabY {
+  float2 yt[MAXSY + 8];  // y-sample s: (hy | F_ADV, ly); F_ADV: its lower tap row is the previous sample's + 1
+};
+struct __align__(16) RoiTab {
+  RoiTabX x;
+  RoiTabY y;
+};
+static_assert(sizeof(RoiTabX) == 672 && sizeof(RoiTabY) == 512 && sizeof(RoiTab) == 1184, "RoiTab layout");
 
 template <typename T>
 struct __align__(128) WarpArea {
 #ifndef UNIT_FWD_DIRECT  // experiment: lanes store straight to global memory, no staging block (more warps fit)
   T stage[CS * P * P];
 #endif
-  RoiTab tab;
+  RoiTabX tx;
+  RoiTabY ty[2];
   uint64_t bar;
 };
 
@@ -146,11 +160,11 @@ roi_tables_kernel(const float* __restrict__ rois, RoiTab* __restrict__ tabs, int
           width = max(width, d + 2);
         }
       }
-      t->bx[lane] = bx;
+      t->x.bx[lane] = bx;
 #pragma unroll
-      for (int j = 0; j < MAXB; ++j) t->wb[j][lane] = w[j];
+      for (int j = 0; j < MAXB; ++j) t->x.wb[j][lane] = w[j];
     }
-    // ---- y: samples in order, with the "lower tap row advances after this sample" and "last sample of its bin" flags
+    // ---- y: samples in order; F_ADV marks a sample whose lower tap row is one past the previous sample's
     const int nsy = P * g.gh;
     const float inv_gh = 1.f / (float)g.gh;
     int y0 = 0, last_lo = 0;
@@ -159,12 +173,13 @@ roi_tables_kernel(const float* __restrict__ rois, RoiTab* __restrict__ tabs, int
       int lo2[2] = {0x3fffffff, 0x3fffffff};
       float hh = 0.f, ll = 0.f;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {  // k = 0: this sample, k = 1: the next one (its lower tap row only)
-        if (s + k < nsy) {
+      for (int k = 0; k < 2; ++k) {  // k = 0: this sample, k = 1: the previous one (its lower tap row only)
+        const int sk = s - k;
+        if (sk >= 0 && sk < nsy) {
           int hi;
           float l, h;
-          const int ph = (int)(((float)(s + k) + 0.5f) * inv_gh);
-          axis_tap(sample_coord(g.start_h, g.bin_h, ph, s + k - ph * g.gh, g.gh), H, lo2[k], hi, l, h);
+          const int ph = (int)(((float)sk + 0.5f) * inv_gh);
+          axis_tap(sample_coord(g.start_h, g.bin_h, ph, sk - ph * g.gh, g.gh), H, lo2[k], hi, l, h);
           if (lo2[k] >= H - 1) {
             lo2[k] = H - 2;
             l = h;
@@ -177,12 +192,10 @@ roi_tables_kernel(const float* __restrict__ rois, RoiTab* __restrict__ tabs, int
         }
       }
       if (s < nsy) {
-        const bool adv = (s == nsy - 1) || (lo2[1] != lo2[0]);
-        if (s < nsy - 1 && (lo2[1] - lo2[0] > 1 || lo2[1] < lo2[0])) bad = true;
-        const int ph = (int)(((float)s + 0.5f) * inv_gh);
-        const bool end = (s - ph * g.gh) == g.gh - 1;
-        const uint32_t bits = (__float_as_uint(hh) & ~3u) | (adv ? F_ADV : 0u) | (end ? F_END : 0u);
-        t->yt[s] = make_float2(__uint_as_float(bits), ll);
+        const bool adv = s > 0 && lo2[0] != lo2[1];
+        if (s > 0 && (lo2[0] - lo2[1] > 1 || lo2[0] < lo2[1])) bad = true;
+        const uint32_t bits = (__float_as_uint(hh) & ~1u) | (adv ? F_ADV : 0u);
+        t->y.yt[s] = make_float2(__uint_as_float(bits), ll);
       }
       if (s0 == 0) y0 = __shfl_sync(0xffffffffu, lo2[0], 0);
       const int src = min(nsy - 1 - s0, 31);
@@ -190,22 +203,53 @@ roi_tables_kernel(const float* __restrict__ rois, RoiTab* __restrict__ tabs, int
     }
     width = __reduce_max_sync(0xffffffffu, width);
     if (lane == 0) {
-      t->y0 = y0;
-      t->nrows = last_lo + 2 - y0;
-      t->nsy = nsy;
-      t->nb = width;
+      t->x.y0 = y0;
+      t->x.nrows = last_lo + 2 - y0;
+      t->x.nb = width;
     }
   }
   if (__any_sync(0xffffffffu, bad)) mode = 2;
+  __syncwarp();  // bx[] written above is visible to lane 0
   if (lane == 0) {
-    t->mode = mode;
-    t->gw = g.gw;
-    t->gh = g.gh;
-    t->inv_count = 1.f / g.count;
-    t->start_w = g.start_w;
-    t->start_h = g.start_h;
-    t->bin_w = g.bin_w;
-    t->bin_h = g.bin_h;
+    // ---- lane map (see RoiTabX::lmap).  Bank group of item (pw, half) = (bx[pw] + half * qs) mod 8 with qs = 1 (mod 8)
+    // sixteen-byte units between the quad planes; rows and band taps shift every lane alike.
+    int unit_at[4][8], cnt[4], first[4];
+    unsigned char slot[4][8];
+    for (int ph = 0; ph < 4; ++ph) {
+      cnt[ph] = 0;
+      first[ph] = 0;
+      for (int k = 0; k < 8; ++k) unit_at[ph][k] = -1;
+    }
+    for (int i = 0; i < 2 * P; ++i) {
+      const int pw = i % P, half = i / P;
+      const int u = (mode == 1 ? t->x.bx[pw] : pw) + half * 4097;  // distinct per (pixel, half); 4097 = 1 (mod 8)
+      const int r = u & 7;
+      int best = -1, best_score = 1 << 30;
+      for (int ph = 0; ph < 4; ++ph) {
+        if (cnt[ph] >= 8) continue;
+        // same pixel already in the phase: free (broadcast); empty bank group: free; otherwise one more wavefront
+        const int cost = unit_at[ph][r] == u ? 0 : (unit_at[ph][r] < 0 ? 1 : 100);
+        const int score = cost * 16 + cnt[ph];
+        if (score < best_score) {
+          best_score = score;
+          best = ph;
+        }
+      }
+      if (unit_at[best][r] < 0) unit_at[best][r] = u;
+      slot[best][cnt[best]++] = (unsigned char)(pw | (half << 4));
+    }
+    for (int ph = 0; ph < 4; ++ph)
+      for (int k = 0; k < 8; ++k)
+        t->x.lmap[8 * ph + k] = k < cnt[ph] ? slot[ph][k] : (unsigned char)(slot[ph][0] | 0x80);
+    (void)first;
+    t->x.mode = mode;
+    t->x.gw = g.gw;
+    t->x.gh = g.gh;
+    t->x.inv_count = 1.f / g.count;
+    t->x.start_w = g.start_w;
+    t->x.start_h = g.start_h;
+    t->x.bin_w = g.bin_w;
+    t->x.bin_h = g.bin_h;
   }
 }
 
@@ -238,67 +282,74 @@ __device__ __forceinline__ void load_slab_quad(const T* __restrict__ src, float4
 
 // ------------------------------------------------------------------------------------------------ lane tasks
 // NB > 0: band width known at compile time; NB == 0: any width <= MAXB (warp-uniform nb).
-// Software pipelined by hand: the next row's pixels and the next y-sample are requested before the current ones are
-// consumed, and the two taps of a sample accumulate in separate chains (the warp is latency-, not throughput-bound).
-template <typename T, int NB>
-__device__ __forceinline__ void task_band(const float4* __restrict__ rowp, int W, int nrows, int nb,
-                                          const f2 (&w)[MAXB], const float2 (&yent)[4], T* __restrict__ dst,
-                                          bool writer) {
+// GH > 0: y-samples per bin known at compile time; GH == 0: any count <= MAXGY (warp-uniform gh).
+// `yt` is the warp's y-table in shared memory: every lane reads the same entry (one broadcast LDS.64 per sample).
+template <typename T>
+__device__ __forceinline__ void store4(T* __restrict__ dst, f2 a, f2 b, bool writer) {
+  if (writer) {
+    const float2 x = unpack2(a), y = unpack2(b);
+    stf(dst, x.x);
+    stf(dst + P * P, x.y);
+    stf(dst + 2 * P * P, y.x);
+    stf(dst + 3 * P * P, y.y);
+  }
+}
+
+template <typename T, int NB, int GH>
+__device__ __forceinline__ void task_band(const float4* __restrict__ rowp, int W, int gh, int nb,
+                                          const float (&w)[MAXB], const float2* __restrict__ yt,
+                                          T* __restrict__ dst, bool writer) {
   constexpr int NV = NB > 0 ? NB : MAXB;
-  f2 hcA = 0ull, hcB = 0ull, oA = 0ull, oB = 0ull, uA = 0ull, uB = 0ull;
-  int s = 0;
-  float2 cur = yent[0];
-  float ex = __shfl_sync(0xffffffffu, cur.x, 0);
-  float ey = __shfl_sync(0xffffffffu, cur.y, 0);
   float4 v[NV];
+  auto load_row = [&]() {
 #pragma unroll
-  for (int j = 0; j < NV; ++j)
-    if (NB > 0 || j < nb) v[j] = rowp[j];
-  for (int r = 0; r < nrows; ++r) {
-    f2 hA = 0ull, hB = 0ull;
+    for (int j = 0; j < NV; ++j)
+      if (NB > 0 || j < nb) v[j] = rowp[j];
+    rowp += W;
+  };
+  auto row_sum = [&](f2& hA, f2& hB) {
+    hA = hB = 0ull;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       if (NB > 0 || j < nb) {
-        fma2(hA, w[j], pack2(v[j].x, v[j].y));
-        fma2(hB, w[j], pack2(v[j].z, v[j].w));
+        const f2 wj = pack2(w[j], w[j]);
+        fma2(hA, wj, pack2(v[j].x, v[j].y));
+        fma2(hB, wj, pack2(v[j].z, v[j].w));
       }
     }
-    rowp += W;
-    if (r + 1 < nrows) {
+  };
+  // prologue: the two rows under the first sample, and the pixels of the row after them are already on their way
+  f2 hcA, hcB, hnA, hnB;
+  load_row();
+  row_sum(hcA, hcB);
+  load_row();
+  row_sum(hnA, hnB);
+  load_row();  // one row ahead; a read past the footprint stays inside the slab / work areas and is never used
+  const int ng = GH > 0 ? GH : gh;
+  float2 en = *yt;  // the table entry is requested one sample ahead (the table has spare entries past the last one)
+#pragma unroll 1
+  for (int ph = 0; ph < P; ++ph) {
+    f2 aA = 0ull, aB = 0ull;
 #pragma unroll
-      for (int j = 0; j < NV; ++j)
-        if (NB > 0 || j < nb) v[j] = rowp[j];
-    }
-    if (r > 0) {
-      bool adv;
-      do {  // the y-samples whose lower tap is row r-1: out += hy * h(r-1) + ly * h(r)
-        const float cx = ex, cy = ey;
-        ++s;
-        if ((s & 31) == 0) cur = (s >> 5) == 1 ? yent[1] : ((s >> 5) == 2 ? yent[2] : yent[3]);
-        ex = __shfl_sync(0xffffffffu, cur.x, s & 31);
-        ey = __shfl_sync(0xffffffffu, cur.y, s & 31);
-        const uint32_t bits = __float_as_uint(cx);
-        adv = (bits & F_ADV) != 0u;
-        const f2 hy = pack2(cx, cx), ly = pack2(cy, cy);
-        fma2(oA, hy, hcA);
-        fma2(oB, hy, hcB);
-        fma2(uA, ly, hA);
-        fma2(uB, ly, hB);
-        if (bits & F_END) {
-          if (writer) {
-            const float2 a = unpack2(oA), b = unpack2(oB), c = unpack2(uA), d = unpack2(uB);
-            stf(dst, a.x + c.x);
-            stf(dst + P * P, a.y + c.y);
-            stf(dst + 2 * P * P, b.x + d.x);
-            stf(dst + 3 * P * P, b.y + d.y);
-          }
-          dst += P;
-          oA = oB = uA = uB = 0ull;
+    for (int i = 0; i < (GH > 0 ? GH : MAXGY); ++i) {
+      if (GH > 0 || i < ng) {
+        const float2 e = en;
+        en = *++yt;
+        if (__float_as_uint(e.x) & F_ADV) {  // warp-uniform
+          hcA = hnA;
+          hcB = hnB;
+          row_sum(hnA, hnB);
+          load_row();
         }
-      } while (!adv);
+        const f2 hy = pack2(e.x, e.x), ly = pack2(e.y, e.y);
+        fma2(aA, hy, hcA);
+        fma2(aB, hy, hcB);
+        fma2(aA, ly, hnA);
+        fma2(aB, ly, hnB);
+      }
     }
-    hcA = hA;
-    hcB = hB;
+    store4<T>(dst, aA, aB, writer);
+    dst += P;
   }
 }
 
@@ -335,7 +386,7 @@ __device__ __noinline__ void task_direct(const float4* __restrict__ q, int H, in
 
 __host__ __device__ inline int quad_stride(int HW) {
   int s = HW + MAXB;  // zero padding: zero-weight band columns of the last row read past the plane
-  while ((s & 7) != 4) ++s;  // the two quads of a pixel column land 64 bytes apart modulo 128
+  while ((s & 7) != 1) ++s;  // quad planes one bank group apart: best fit for the lane map (roi_tables_kernel)
   return s;
 }
 
@@ -354,15 +405,8 @@ __global__ void __launch_bounds__(NT, 1) roi_align_fwd_band(const Params p, cons
   const int nslab = p.C / CS;
   const T* feat = reinterpret_cast<const T*>(p.feat);
   T* out = reinterpret_cast<T*>(p.out);
-  // lanes 28..31 shadow lane 27 (they take part in the shuffles) and never store
-  const bool writer = lane < 2 * P;
-  const int wl = writer ? lane : 2 * P - 1;
-  const int half = wl >= P ? 1 : 0, pw = wl - half * P;
-  const float4* quad = slab + (size_t)half * qs;
-#ifndef UNIT_FWD_DIRECT
-  T* stage_lane = wa->stage + (4 * half) * (P * P) + pw;
-#endif
   uint32_t parity = 0;
+  int ycur = 0;  // y-table buffer of the RoI being computed
 
   for (int i = tid; i < NQ * (qs - HW); i += NT) {
     const int q = i / (qs - HW), o = i - q * (qs - HW);
@@ -396,35 +440,46 @@ __global__ void __launch_bounds__(NT, 1) roi_align_fwd_band(const Params p, cons
       if (lane == 0) r = atomicAdd(&s_next, 1);
       return __shfl_sync(0xffffffffu, r, 0);
     };
-    auto issue_tab = [&](int r) {
+    auto issue_tab = [&](int r, int yb) {  // x-part into the single buffer, y-part into y buffer `yb`
       if (lane == 0) {
         mbar_expect_tx(&wa->bar, (uint32_t)sizeof(RoiTab));
-        bulk_load(&wa->tab, tabs + r_base + r, (uint32_t)sizeof(RoiTab), &wa->bar);
+        bulk_load(&wa->tx, &tabs[r_base + r].x, (uint32_t)sizeof(RoiTabX), &wa->bar);
+        bulk_load(&wa->ty[yb], &tabs[r_base + r].y, (uint32_t)sizeof(RoiTabY), &wa->bar);
       }
     };
     int cur = fetch();
-    if (cur < r1) issue_tab(cur);
+    if (cur < r1) issue_tab(cur, ycur);
     while (cur < r1) {
       mbar_wait(&wa->bar, parity);
       parity ^= 1u;
-      // ---- consume the table into registers
-      const RoiTab* t = &wa->tab;
-      const int mode = t->mode, gw = t->gw, gh = t->gh, nb = t->nb, y0 = t->y0, nrows = t->nrows;
-      const float inv_count = t->inv_count, start_w = t->start_w, start_h = t->start_h, bin_w = t->bin_w,
-                  bin_h = t->bin_h;
+      // ---- consume the x-part into registers; the y-part stays in its buffer for the walk
+      const RoiTabX* t = &wa->tx;
+      const int mode = t->mode, gw = t->gw, gh = t->gh, nb = t->nb, y0 = t->y0;
+      // which (output column, channel quad) this lane owns for this RoI; 4 lanes shadow an owner and never store
+      const int lm = t->lmap[lane];
+      const bool writer = (lm & 0x80) == 0;
+      const int half = (lm >> 4) & 1, pw = lm & 15;
+      const float4* quad = slab + (size_t)half * qs;
+#ifndef UNIT_FWD_DIRECT
+      T* stage_lane = wa->stage + (4 * half) * (P * P) + pw;
+#endif
       const int bx = t->bx[pw];
-      f2 w[MAXB];
+      float w[MAXB];
 #pragma unroll
-      for (int j = 0; j < MAXB; ++j) {
-        const float wj = t->wb[j][pw];
-        w[j] = pack2(wj, wj);
+      for (int j = 0; j < MAXB; ++j) w[j] = t->wb[j][pw];
+      float inv_count = 0.f, start_w = 0.f, start_h = 0.f, bin_w = 0.f, bin_h = 0.f;
+      if (mode == 2) {
+        inv_count = t->inv_count;
+        start_w = t->start_w;
+        start_h = t->start_h;
+        bin_w = t->bin_w;
+        bin_h = t->bin_h;
       }
-      float2 yent[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) yent[j] = (32 * j + lane < MAXSY) ? t->yt[32 * j + lane] : make_float2(0.f, 0.f);
-      __syncwarp();  // the table buffer is free: fetch the next RoI and start loading its table
+      const float2* yt = wa->ty[ycur].yt;
+      __syncwarp();  // the x buffer is free: fetch the next RoI and start loading its tables
       const int nxt = fetch();
-      if (nxt < r1) issue_tab(nxt);
+      if (nxt < r1) issue_tab(nxt, ycur ^ 1);
+      ycur ^= 1;
 #ifndef UNIT_FWD_DIRECT
       if (lane == 0) v2::bulk_wait_read_all();  // the previous bulk store has drained this warp's staging block
       __syncwarp();
@@ -434,10 +489,18 @@ __global__ void __launch_bounds__(NT, 1) roi_align_fwd_band(const Params p, cons
       if (!(p.debug & 1)) {
         if (mode == 1) {
           const float4* rowp = quad + (size_t)y0 * p.W + bx;
-          if (nb <= 2) task_band<T, 2>(rowp, p.W, nrows, nb, w, yent, stage_lane, writer);
-          else if (nb == 3) task_band<T, 3>(rowp, p.W, nrows, nb, w, yent, stage_lane, writer);
-          else if (nb == 4) task_band<T, 4>(rowp, p.W, nrows, nb, w, yent, stage_lane, writer);
-          else task_band<T, 0>(rowp, p.W, nrows, nb, w, yent, stage_lane, writer);
+#define UNIT_BAND_CASE(NBV)                                                                            \
+  {                                                                                                    \
+    if (gh == 1) task_band<T, NBV, 1>(rowp, p.W, gh, nb, w, yt, stage_lane, writer);                   \
+    else if (gh == 2) task_band<T, NBV, 2>(rowp, p.W, gh, nb, w, yt, stage_lane, writer);              \
+    else task_band<T, NBV, 0>(rowp, p.W, gh, nb, w, yt, stage_lane, writer);                           \
+  }
+          if (nb <= 2) UNIT_BAND_CASE(2)
+          else if (nb == 3) UNIT_BAND_CASE(3)
+          else if (nb == 4) UNIT_BAND_CASE(4)
+          else if (nb == 5) UNIT_BAND_CASE(5)
+          else UNIT_BAND_CASE(0)
+#undef UNIT_BAND_CASE
         } else if (mode == 2) {
           if (writer) task_direct<T>(quad, p.H, p.W, gw, gh, inv_count, start_w, start_h, bin_w, bin_h, pw, stage_lane);
         } else if (writer) {

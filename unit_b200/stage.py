@@ -42,10 +42,12 @@ class RoIStage:
         return head.box_predictor.inference(predictions, proposals)
 
     @torch.no_grad()
-    def infer_graphed(self, features: torch.Tensor, proposals: List[Instances]):
+    def infer_graphed(self, features: torch.Tensor, proposals: List[Instances], padded: bool = False):
         """``infer`` with everything up to the padded detections replayed from one CUDA graph (keyed by the input
         buffers, which the caller must reuse); the only host work per call is the read of the detection counts.  The
-        returned Instances are views of the graph's static outputs: consume them before the next call with that key."""
+        returned Instances are views of the graph's static outputs: consume them before the next call with that key.
+        ``padded=True`` skips that host read and returns the device tuple (det_boxes [n,topk,4], det_scores,
+        det_classes, det_roi, det_counts) -- what ``distributed.gather_detections`` takes."""
         head = self.head
         head.move_mappings_to_gpu()
         key = ("infer", features.data_ptr(), tuple(features.shape),
@@ -76,6 +78,8 @@ class RoIStage:
             st = (graph, dets)
             self._graphs[key] = st
         st[0].replay()
+        if padded:
+            return st[1]
         return layers.instances_from_detections(st[1], [p.image_size for p in proposals])
 
     @torch.no_grad()
