@@ -750,7 +750,7 @@ def run_ours(args):
             "value": N_IMG / wall, "unit": "images/s", "cores": cores, "kind": "port",
             "sample": f"ONE full step measured by wall clock, nothing scaled ({wall:.1f}s: label+sample {tl * 1e3:.1f} ms, "
                       f"ROIAlign fwd+bwd over all 2x512 RoIs {tr:.2f}s, transfer+loss+backward {tp * 1e3:.1f} ms); "
-                      f"`--impl reference` times {{steps}} such steps",
+                      f"`bench.py --impl reference` times K such steps",
         }
 
     if rank == 0:
