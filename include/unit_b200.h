@@ -128,6 +128,12 @@ int unit_fastrcnn_loss(const float* scores, const float* deltas, const float* pr
                        const int64_t* gt_classes, int R, int K, float wx, float wy, float ww, float wh,
                        float smooth_l1_beta, float* losses, float* d_scores, float* d_deltas, void* workspace,
                        size_t workspace_bytes, unit_stream_t stream);
+/* Same, with both gradients written into ONE packed buffer d_packed[R, ld_packed] = [d_scores (K+1) | d_deltas (4K) |
+ * zeros]: the layout unit_predictor_wgrad consumes (ld_packed >= 128 there). */
+int unit_fastrcnn_loss_packed(const float* scores, const float* deltas, const float* proposals, const float* gt_boxes,
+                              const int64_t* gt_classes, int R, int K, float wx, float wy, float ww, float wh,
+                              float smooth_l1_beta, float* losses, float* d_packed, int ld_packed, void* workspace,
+                              size_t workspace_bytes, unit_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * fast_rcnn_inference for a batch of images in two launches.  Replaces [D2] fast_rcnn_inference(_single_image)
@@ -188,6 +194,8 @@ typedef struct {
   /* row strides (in floats) of delta_scores / proposal_deltas / ft_scores / ft_deltas, so that column blocks of one
    * packed GEMM output can be passed without a copy; 0 = dense (K+1 resp. 4K) */
   int ld_delta_scores, ld_proposal_deltas, ld_ft_scores, ld_ft_deltas;
+  /* same for vis_logits / weak_scores (0 = dense K+1) */
+  int ld_vis_logits, ld_weak_scores;
 } unit_transfer_params;
 int unit_similarity_transfer(const unit_transfer_params* p, const float* vis_logits, const float* static_cls,
                              const float* static_bbox, const float* static_seg, const int* base, const int* novel,
@@ -217,6 +225,27 @@ int unit_similarity_transfer_bwd_vis(const unit_transfer_params* p, const float*
 size_t unit_predictor_gemm_workspace_bytes(int M, int N, int K);
 int unit_predictor_gemm(const float* x, const float* w, const float* bias, float* y, int M, int N, int K,
                         void* workspace, size_t workspace_bytes, unit_stream_t stream);
+/* Two problems sharing M and K in ONE launch (+ one reduce launch): y1[M,ldy1] = x1 . w1^T + b1 and y2[M,ldy2] = x2 . w2^T
+ * + b2 (N2 == 0: only the first).  Columns n >= N of a padded output row are written as zeros.  This is the packed
+ * [delta | bbox | ft | mean-OICR] product on the box-head features together with the mean-OICR product on the weak
+ * branch's features (fast_rcnn.py:486-494, roi_heads.py:252). */
+size_t unit_predictor_gemm2_workspace_bytes(int M, int N1, int N2, int K);
+int unit_predictor_gemm2(const float* x1, const float* w1, const float* b1, float* y1, int N1, int ldy1,
+                         const float* x2, const float* w2, const float* b2, float* y2, int N2, int ldy2, int M, int K,
+                         void* workspace, size_t workspace_bytes, unit_stream_t stream);
+
+/* Weight / bias gradients of the trainable predictor columns on tcgen05 (TF32, fp32 accumulation in TMEM):
+ *   dW[N,K] = gy[R,N]^T . x[R,K],  db[N] = column sums of gy      (N <= 128; gy rows padded with zeros to ldg >= 128)
+ * Both operands are read as they lie in memory (MN-major UMMA operands: no transposed copies).  Gradient rows
+ * [seg_rows[s], seg_rows[s+1]) go to w_dst[s] ([rows,K] row-major) / b_dst[s], multiplied by the device scalar
+ * *seg_scale[s] when given (the upstream dL/dloss), overwritten or accumulated in place -- i.e. straight into the
+ * parameters' .grad views of the flat all-reduce bucket.  Replaces autograd's Linear backward for cls_score_ft /
+ * bbox_pred_ft (the trainable parameters of fast_rcnn.py:477-482, 527-528). */
+size_t unit_predictor_wgrad_workspace_bytes(int R, int K);
+int unit_predictor_wgrad(const float* gy, int ldg, const float* x, int R, int N, int K, int nseg, const int* seg_rows,
+                         float* const* w_dst, float* const* b_dst, const float* const* seg_scale, int accumulate,
+                         void* workspace, size_t workspace_bytes, unit_stream_t stream);
+
 
 /* ---------------------------------------------------------------------------------------------------------
  * Mask transfer + class select + sigmoid.  Replaces mask_head.py:16-37 / 72-94 and [D2] mask_rcnn_inference.

@@ -22,6 +22,7 @@ class TransferParams(Structure):
         ("norm_cls", c_int), ("norm_bbox", c_int), ("norm_seg", c_int),
         ("do_transfer", c_int), ("novel_neg_inf", c_int), ("static_per_roi", c_int),
         ("ld_delta_scores", c_int), ("ld_proposal_deltas", c_int), ("ld_ft_scores", c_int), ("ld_ft_deltas", c_int),
+        ("ld_vis_logits", c_int), ("ld_weak_scores", c_int),
     ]
 
 
@@ -60,6 +61,13 @@ _SIGNATURES = {
     "unit_mask_paste": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, P, P]),
     "unit_predictor_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "unit_predictor_gemm": (c_int, [P, P, P, P, c_int, c_int, c_int, P, c_size_t, P]),
+    "unit_predictor_gemm2_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "unit_predictor_gemm2": (c_int, [P, P, P, P, c_int, c_int, P, P, P, P, c_int, c_int, c_int, c_int, P, c_size_t, P]),
+    "unit_predictor_wgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "unit_predictor_wgrad": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_void_p),
+                                     POINTER(c_void_p), POINTER(c_void_p), c_int, P, c_size_t, P]),
+    "unit_fastrcnn_loss_packed": (c_int, [P, P, P, P, P, c_int, c_int, c_float, c_float, c_float, c_float, c_float, P, P,
+                                          c_int, P, c_size_t, P]),
     "unit_boxes_to_rois": (c_int, [P, P, c_int, c_int, P, P]),
     "unit_mil_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "unit_mil_loss": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P, c_size_t, P]),

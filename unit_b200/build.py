@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libunit_b200.so")
 STAMP = os.path.join(HERE, ".libunit_b200.stamp")  # git-ignored convenience only; the .so carries its own digest
-SOURCES = ["api.cu", "roi_align.cu", "roi_align_fwd.cu", "roi_align_fwd_band.cu", "roi_align_bwd.cu", "roi_align_bwd_cl.cu", "match.cu", "detect.cu", "transfer.cu", "gemm.cu", "weak.cu"]
+SOURCES = ["api.cu", "roi_align.cu", "roi_align_fwd.cu", "roi_align_fwd_band.cu", "roi_align_bwd.cu", "roi_align_bwd_cl.cu", "roi_align_bwd_cl2.cu", "match.cu", "detect.cu", "transfer.cu", "gemm.cu", "weak.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -46,6 +46,7 @@ const Switches& switches() {
     v.fwd_band_bf16 = getenv("UNIT_ROI_FWD_BAND_BF16") != nullptr;
     v.fwd_v3 = getenv("UNIT_ROI_FWD_V3") != nullptr;
     v.bwd_v4 = getenv("UNIT_ROI_BWD_V4") != nullptr;
+    v.bwd_cl1 = getenv("UNIT_ROI_BWD_CL1") != nullptr;
     v.paste_flat = getenv("UNIT_PASTE_FLAT") != nullptr;
     v.roi_debug = env_int("UNIT_ROI_DEBUG", 0);
     v.bwd_promo = env_int("UNIT_ROI_BWD_PROMO", 2);

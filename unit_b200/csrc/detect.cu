@@ -1083,7 +1083,8 @@ __global__ void fastrcnn_loss_kernel(const float* __restrict__ scores, const flo
                                      const float4* __restrict__ proposals, const float4* __restrict__ gt_boxes,
                                      const int64_t* __restrict__ gt_classes, int R, int K, float wx, float wy,
                                      float ww, float wh, float beta, float* __restrict__ row_loss,
-                                     float* __restrict__ d_scores, float* __restrict__ d_deltas) {
+                                     float* __restrict__ d_scores, float* __restrict__ d_deltas, int ld_ds, int ld_dd,
+                                     int pad_cols) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= R) return;
   const int K1 = K + 1;
@@ -1098,7 +1099,7 @@ __global__ void fastrcnn_loss_kernel(const float* __restrict__ scores, const flo
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float lse = m + logf(sum);
   for (int k = lane; k < K1; k += 32)
-    d_scores[(long long)r * K1 + k] = (expf(s[k] - lse) - (k == cls ? 1.f : 0.f)) * invR;
+    d_scores[(long long)r * ld_ds + k] = (expf(s[k] - lse) - (k == cls ? 1.f : 0.f)) * invR;
   float box_loss = 0.f;
   const bool fg = cls >= 0 && cls < K;
   float dv = 0.f;
@@ -1132,8 +1133,9 @@ __global__ void fastrcnn_loss_kernel(const float* __restrict__ scores, const flo
     float v = 0.f;
     const int j = i - 4 * cls;
     if (fg && j >= 0 && j < 4) v = (j == 0 ? dv0 : j == 1 ? dv1 : j == 2 ? dv2 : dv3) * invR;
-    d_deltas[(long long)r * 4 * K + i] = v;
+    d_deltas[(long long)r * ld_dd + i] = v;
   }
+  for (int i = 4 * K + lane; i < 4 * K + pad_cols; i += 32) d_deltas[(long long)r * ld_dd + i] = 0.f;  // row padding
   box_loss += __shfl_xor_sync(0xffffffffu, box_loss, 1);
   box_loss += __shfl_xor_sync(0xffffffffu, box_loss, 2);
   if (lane == 0) {
@@ -1172,6 +1174,34 @@ __global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int R, fl
 }  // namespace detect
 }  // namespace unit
 
+extern "C" int unit_fastrcnn_loss_packed(const float* scores, const float* deltas, const float* proposals,
+                                         const float* gt_boxes, const int64_t* gt_classes, int R, int K, float wx,
+                                         float wy, float ww, float wh, float smooth_l1_beta, float* losses,
+                                         float* d_packed, int ld_packed, void* workspace, size_t workspace_bytes,
+                                         unit_stream_t stream) {
+  UNIT_REQUIRE(R >= 0 && K > 0, "fastrcnn_loss: bad shape");
+  UNIT_REQUIRE(losses, "fastrcnn_loss: null losses");
+  UNIT_REQUIRE(ld_packed >= 5 * K + 1, "fastrcnn_loss_packed: row stride smaller than (K+1) + 4K");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (R == 0) {
+    UNIT_CUDA(cudaMemsetAsync(losses, 0, 2 * sizeof(float), st));
+    return UNIT_OK;
+  }
+  UNIT_REQUIRE(scores && deltas && proposals && gt_boxes && gt_classes && d_packed, "fastrcnn_loss: null pointer");
+  UNIT_REQUIRE((((uintptr_t)proposals | (uintptr_t)gt_boxes) & 15) == 0, "fastrcnn_loss: boxes must be 16-byte aligned");
+  if (!workspace || workspace_bytes < (size_t)2 * R * sizeof(float)) {
+    set_error("fastrcnn_loss: workspace too small");
+    return UNIT_EWORKSPACE;
+  }
+  unit::detect::fastrcnn_loss_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(
+      scores, deltas, (const float4*)proposals, (const float4*)gt_boxes, gt_classes, R, K, wx, wy, ww, wh,
+      smooth_l1_beta, (float*)workspace, d_packed, d_packed + (K + 1), ld_packed, ld_packed, ld_packed - (5 * K + 1));
+  UNIT_CHECK_LAUNCH("fastrcnn_loss_kernel");
+  unit::detect::loss_reduce_kernel<<<1, 1024, 0, st>>>((const float*)workspace, R, losses);
+  UNIT_CHECK_LAUNCH("loss_reduce_kernel");
+  return UNIT_OK;
+}
+
 extern "C" int unit_fastrcnn_loss(const float* scores, const float* deltas, const float* proposals,
                                   const float* gt_boxes, const int64_t* gt_classes, int R, int K, float wx, float wy,
                                   float ww, float wh, float smooth_l1_beta, float* losses, float* d_scores,
@@ -1192,7 +1222,7 @@ extern "C" int unit_fastrcnn_loss(const float* scores, const float* deltas, cons
   }
   unit::detect::fastrcnn_loss_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(
       scores, deltas, (const float4*)proposals, (const float4*)gt_boxes, gt_classes, R, K, wx, wy, ww, wh,
-      smooth_l1_beta, (float*)workspace, d_scores, d_deltas);
+      smooth_l1_beta, (float*)workspace, d_scores, d_deltas, K + 1, 4 * K, 0);
   UNIT_CHECK_LAUNCH("fastrcnn_loss_kernel");
   unit::detect::loss_reduce_kernel<<<1, 1024, 0, st>>>((const float*)workspace, R, losses);
   UNIT_CHECK_LAUNCH("loss_reduce_kernel");

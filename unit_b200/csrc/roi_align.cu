@@ -135,6 +135,10 @@ bool bwd_cl_fits(int C, int H, int W, int R, int dtype, const void* gout);
 int launch_bwd_cl(const void* gout, const float* rois, void* gfeat, void* ws, int N, int C, int H, int W, int R,
                   float scale, int sr, int aligned, int dtype, cudaStream_t st);
 
+size_t bwd_cl2_table_bytes(int R);
+int launch_bwd_cl2(const void* gout, const float* rois, void* gfeat, void* ws, int N, int C, int H, int W, int R,
+                   float scale, int sr, int aligned, cudaStream_t st);
+
 static size_t offsets_bytes(int N) { return ((size_t)(N + 2) * sizeof(int) + 255) / 256 * 256; }
 
 }  // namespace roi
@@ -147,7 +151,7 @@ extern "C" {
 
 size_t unit_roi_align_workspace_bytes(int N, int C, int H, int W, int R, int dtype) {
   const size_t fwd = fwd_band_workspace_bytes(R);
-  const size_t bwd = bwd_slab2_workspace_bytes(N, C, H, W, dtype);
+  const size_t bwd = bwd_slab2_workspace_bytes(N, C, H, W, dtype) + 512 + bwd_cl2_table_bytes(R);
   return offsets_bytes(N) + (fwd > bwd ? fwd : bwd) + 256;
 }
 
@@ -220,11 +224,14 @@ int unit_roi_align_bwd(const void* grad_out, const float* rois, void* grad_feat,
     return UNIT_OK;
   }
   if (PH == 14 && PW == 14 && bwd_cl_fits(C, H, W, R, dtype, grad_out) && !switches().bwd_v4) {
-    const size_t need = offsets_bytes(N) + bwd_slab2_workspace_bytes(N, C, H, W, dtype);
+    const size_t need = offsets_bytes(N) + bwd_slab2_workspace_bytes(N, C, H, W, dtype) + 512 + bwd_cl2_table_bytes(R);
     if (!workspace || workspace_bytes < need) {
       set_error("roi_align_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
       return UNIT_EWORKSPACE;
     }
+    if (dtype == UNIT_F32 && !switches().bwd_cl1)  // table-driven channel-lane kernel (fp32 I/O)
+      return launch_bwd_cl2(grad_out, rois, grad_feat, (char*)workspace + offsets_bytes(N), N, C, H, W, R,
+                            spatial_scale, sampling_ratio, aligned, st);
     return launch_bwd_cl(grad_out, rois, grad_feat, (char*)workspace + offsets_bytes(N), N, C, H, W, R, spatial_scale,
                          sampling_ratio, aligned, dtype, st);
   }

@@ -582,6 +582,17 @@ static EncodeTiledFn encode_fn() {
 
 }  // namespace cl
 
+// epilogue kernels shared with roi_align_bwd_cl2.cu
+void launch_bwd_cl_zero(void* ws, long long n4, cudaStream_t st) {
+  const int zgrid = (int)std::min<long long>((n4 + 255) / 256, (long long)sm_count() * 8);
+  cl::zero4_kernel<<<zgrid, 256, 0, st>>>((float4*)ws, n4);
+}
+void launch_bwd_cl_unpermute(const float* scratch, void* gfeat, int N, int C, int HW, bool bf16, cudaStream_t st) {
+  dim3 tgrid((HW + 31) / 32, C / cl::CB, N);
+  if (bf16) cl::unpermute_kernel<true><<<tgrid, 256, 0, st>>>(scratch, gfeat, C, HW);
+  else cl::unpermute_kernel<false><<<tgrid, 256, 0, st>>>(scratch, gfeat, C, HW);
+}
+
 bool bwd_cl_fits(int C, int H, int W, int R, int dtype, const void* gout) {
   return (dtype == UNIT_F32 || dtype == UNIT_BF16) && (C % cl::CB) == 0 && H >= 2 && W >= 2 &&
          ((uintptr_t)gout & 15) == 0 &&

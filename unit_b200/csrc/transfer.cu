@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(TT) similarity_transfer_kernel(const TransferA
   const bool need_v = a.p.do_transfer && (a.p.wv_cls != 0.f || a.p.wv_bbox != 0.f || a.p.wv_seg != 0.f);
   if (need_v) {
     // softmax over all K+1 OICR logits, base columns, renormalise, threshold (roi_heads.py:255-257)
-    const float* vl = a.vis_logits + (long long)r * K1;
+    const float* vl = a.vis_logits + (long long)r * (a.p.ld_vis_logits ? a.p.ld_vis_logits : K1);
     if (warp == 0) {
       float m = -INFINITY;
       for (int k = lane; k < K1; k += 32) m = fmaxf(m, vl[k]);
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(TT) similarity_transfer_kernel(const TransferA
     float v = s_delta[k];
     const int kind = k < K ? a.class_kind[k] : -1;
     if (a.p.do_transfer && kind >= NOVEL_TAG) v = v + s_tc[kind - NOVEL_TAG];
-    if (a.weak_scores) v = v + a.weak_scores[(long long)r * K1 + k];
+    if (a.weak_scores) v = v + a.weak_scores[(long long)r * (a.p.ld_weak_scores ? a.p.ld_weak_scores : K1) + k];
     if (a.ft_scores) v = v + a.ft_scores[r * ld_fs + k];
     if (a.p.novel_neg_inf && kind >= NOVEL_TAG) v = -INFINITY;
     a.out_scores[(long long)r * K1 + k] = v;
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(TT) similarity_transfer_bwd_vis_kernel(const T
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = TT / 32;
   const long long ld_d = a.p.ld_delta_scores ? a.p.ld_delta_scores : K1;
   const long long ld_p = a.p.ld_proposal_deltas ? a.p.ld_proposal_deltas : 4 * K;
-  const float* vl = a.vis_logits + (long long)r * K1;
+  const float* vl = a.vis_logits + (long long)r * (a.p.ld_vis_logits ? a.p.ld_vis_logits : K1);
   for (int b = tid; b < B; b += TT) s_gv[b] = 0.f;
   if (warp == 0) {
     float m = -INFINITY;
@@ -611,7 +611,9 @@ int unit_similarity_transfer(const unit_transfer_params* p, const float* vis_log
   UNIT_REQUIRE((p->ld_delta_scores == 0 || p->ld_delta_scores >= p->K + 1) &&
                    (p->ld_proposal_deltas == 0 || p->ld_proposal_deltas >= 4 * p->K) &&
                    (p->ld_ft_scores == 0 || p->ld_ft_scores >= p->K + 1) &&
-                   (p->ld_ft_deltas == 0 || p->ld_ft_deltas >= 4 * p->K),
+                   (p->ld_ft_deltas == 0 || p->ld_ft_deltas >= 4 * p->K) &&
+                   (p->ld_vis_logits == 0 || p->ld_vis_logits >= p->K + 1) &&
+                   (p->ld_weak_scores == 0 || p->ld_weak_scores >= p->K + 1),
                "similarity_transfer: a row stride is smaller than its row");
   TransferArgs a;
   a.p = *p;

@@ -565,8 +565,7 @@ def similarity_transfer_forward(spec: TransferSpec, vis_logits, delta_scores, pr
 
     (delta_scores, ld_d), (proposal_deltas, ld_p) = rows(delta_scores), rows(proposal_deltas)
     (ft_scores, ld_fs), (ft_deltas, ld_fd) = rows(ft_scores), rows(ft_deltas)
-    cv = lambda t: None if t is None else _c(t, _F32)
-    vis_logits, weak_scores = cv(vis_logits), cv(weak_scores)
+    (vis_logits, ld_v), (weak_scores, ld_w) = rows(vis_logits), rows(weak_scores)
     out_scores = torch.empty(tuple(delta_scores.shape), dtype=_F32, device=dev)
     out_bbox = torch.empty(tuple(proposal_deltas.shape), dtype=_F32, device=dev)
     sims = {h: (torch.empty((R, spec.Nn, spec.B), dtype=_F32, device=dev) if h in want_similarity else None)
@@ -574,6 +573,7 @@ def similarity_transfer_forward(spec: TransferSpec, vis_logits, delta_scores, pr
     if R:
         p = spec.params(R, do_transfer, novel_neg_inf)
         p.ld_delta_scores, p.ld_proposal_deltas, p.ld_ft_scores, p.ld_ft_deltas = ld_d, ld_p, ld_fs, ld_fd
+        p.ld_vis_logits, p.ld_weak_scores = ld_v, ld_w
         check(lib().unit_similarity_transfer(ctypes.byref(p), _ptr(vis_logits), _ptr(spec.static.get("cls")),
                                              _ptr(spec.static.get("bbox")), _ptr(spec.static.get("seg")),
                                              _ptr(spec.base_i32), _ptr(spec.novel_i32), _ptr(spec.class_kind),
@@ -611,9 +611,10 @@ def similarity_transfer_backward_vis(spec: TransferSpec, vis_logits, delta_score
             return _c(t, _F32), 0
 
         (delta_scores, ld_d), (proposal_deltas, ld_p) = rows(delta_scores), rows(proposal_deltas)
+        vis_logits, ld_v = rows(vis_logits)
         p = spec.params(R, True, False)
-        p.ld_delta_scores, p.ld_proposal_deltas = ld_d, ld_p
-        check(lib().unit_similarity_transfer_bwd_vis(ctypes.byref(p), _ptr(_c(vis_logits, _F32)),
+        p.ld_delta_scores, p.ld_proposal_deltas, p.ld_vis_logits = ld_d, ld_p, ld_v
+        check(lib().unit_similarity_transfer_bwd_vis(ctypes.byref(p), _ptr(vis_logits),
                                                      _ptr(spec.static.get("cls")), _ptr(spec.static.get("bbox")),
                                                      _ptr(spec.base_i32), _ptr(spec.novel_i32), _ptr(delta_scores),
                                                      _ptr(proposal_deltas), _ptr(_c(g_scores, _F32)),
@@ -741,6 +742,140 @@ class _LinearTF32Fn(torch.autograd.Function):
 
 def linear_tf32(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     return _LinearTF32Fn.apply(x, w, bias)
+
+
+def predictor_gemm2(x1: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], x2: Optional[torch.Tensor] = None,
+                    w2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None):
+    """Two products sharing M and K in ONE tcgen05 launch (+ one reduce launch):
+    y1 = x1 @ w1.T + b1 and y2 = x2 @ w2.T + b2.  Output rows are padded to a multiple of 32 columns (zeros), so
+    column blocks can be handed on as (pointer, row stride) views.  Returns (y1, y2 or None)."""
+    dev = _need_cuda(x1, w1)
+    x1, w1 = _c(x1, _F32), _c(w1, _F32)
+    M, K = x1.shape
+    N1 = w1.shape[0]
+    ld1 = (N1 + 31) // 32 * 32
+    y1 = torch.empty((M, ld1), dtype=_F32, device=dev)
+    N2, ld2, y2 = 0, 0, None
+    if x2 is not None:
+        x2, w2 = _c(x2, _F32), _c(w2, _F32)
+        N2 = w2.shape[0]
+        ld2 = (N2 + 31) // 32 * 32
+        y2 = torch.empty((M, ld2), dtype=_F32, device=dev)
+    if M == 0:
+        return y1, y2
+    cb = lambda t: None if t is None else _c(t, _F32)
+    b1, b2 = cb(b1), cb(b2)
+    ws = _workspace(dev, lib().unit_predictor_gemm2_workspace_bytes(M, N1, N2, K))
+    check(lib().unit_predictor_gemm2(_ptr(x1), _ptr(w1), _ptr(b1), _ptr(y1), N1, ld1, _ptr(x2), _ptr(w2), _ptr(b2),
+                                     _ptr(y2), N2, ld2, M, K, _ptr(ws), ws.numel(), _stream()), "unit_predictor_gemm2")
+    return y1, y2
+
+
+def predictor_wgrad(gy: torch.Tensor, x: torch.Tensor, n_cols: int, seg_rows: Sequence[int],
+                    w_dst: Sequence[Optional[torch.Tensor]], b_dst: Sequence[Optional[torch.Tensor]],
+                    scales: Sequence[Optional[torch.Tensor]], accumulate: bool) -> None:
+    """dW = gy[:, :n_cols].T @ x and db = gy[:, :n_cols].sum(0) on the tcgen05 tensor cores, written (or accumulated)
+    straight into the destination buffers per row segment -- normally the parameters' ``.grad`` views of the flat
+    all-reduce bucket.  ``gy`` is [R, ld] with ld a multiple of 128 and zeros past ``n_cols``; ``scales[s]`` is a
+    device scalar multiplying segment s (the upstream gradient of its loss)."""
+    dev = _need_cuda(gy, x)
+    assert gy.dtype == _F32 and gy.dim() == 2 and gy.stride(1) == 1 and gy.stride(0) % 128 == 0
+    x = _c(x, _F32)
+    R, K = x.shape
+    ld = gy.stride(0)
+    ws = _workspace(dev, lib().unit_predictor_wgrad_workspace_bytes(R, K))
+    seg_rows = [int(v) for v in seg_rows]
+    for n0 in range(0, n_cols, 128):  # the kernel handles <= 128 gradient rows per launch (one UMMA M tile)
+        n1 = min(n_cols, n0 + 128)
+        rows, wd, bd, sc = [0], [], [], []
+        for s in range(len(seg_rows) - 1):
+            a, b = max(seg_rows[s], n0), min(seg_rows[s + 1], n1)
+            if a >= b:
+                continue
+            rows.append(b - n0)
+            off = a - seg_rows[s]
+            wd.append(None if w_dst[s] is None else w_dst[s][off:])
+            bd.append(None if b_dst[s] is None else b_dst[s][off:])
+            sc.append(scales[s])
+        nseg = len(rows) - 1
+        c_rows = (ctypes.c_int * (nseg + 1))(*rows)
+        vp = lambda ts: (ctypes.c_void_p * nseg)(*[None if t is None else t.data_ptr() for t in ts])
+        g = gy[:, n0:]
+        check(lib().unit_predictor_wgrad(ctypes.c_void_p(g.data_ptr()), ld, _ptr(x), R, n1 - n0, K, nseg, c_rows, vp(wd),
+                                         vp(bd), vp(sc), int(bool(accumulate)), _ptr(ws), ws.numel(), _stream()),
+              "unit_predictor_wgrad")
+
+
+def fastrcnn_loss_packed(scores, deltas, proposals, gt_boxes, gt_classes, weights=(10.0, 10.0, 5.0, 5.0), beta=0.0):
+    """FastRCNNOutputs.losses with both gradients in one packed, zero-padded buffer:
+    -> (losses [2], d_packed [R, ld] = [dL_cls/dscores | dL_box/ddeltas | 0], ld = multiple of 128)."""
+    dev = _need_cuda(scores, deltas)
+    scores, deltas = _c(scores, _F32), _c(deltas, _F32)
+    R, K1 = scores.shape
+    K = K1 - 1
+    ld = (5 * K + 1 + 127) // 128 * 128
+    losses = torch.empty((2,), dtype=_F32, device=dev)
+    d_packed = torch.empty((R, ld), dtype=_F32, device=dev)
+    ws = _workspace(dev, max(R, 1) * 8)
+    check(lib().unit_fastrcnn_loss_packed(_ptr(scores), _ptr(deltas), _ptr(_c(proposals, _F32)), _ptr(_c(gt_boxes, _F32)),
+                                          _ptr(_c(gt_classes, torch.int64)), R, K, float(weights[0]), float(weights[1]),
+                                          float(weights[2]), float(weights[3]), float(beta), _ptr(losses),
+                                          _ptr(d_packed), ld, _ptr(ws), ws.numel(), _stream()),
+          "unit_fastrcnn_loss_packed")
+    return losses, d_packed
+
+
+class _FTStepLossFn(torch.autograd.Function):
+    """The fine-tune predictor + losses as ONE autograd node (fast_rcnn.py:484-533 followed by FastRCNNOutputs.losses):
+    packed tcgen05 GEMM [delta | bbox | ft | mean-OICR](x) and mean-OICR(x_weak) -> fused similarity + transfer ->
+    fused CE + smooth-L1 (+ their gradients).  Backward is one tcgen05 weight-gradient GEMM that writes the gradients
+    of cls_score_ft / bbox_pred_ft (scaled by the upstream loss gradients) directly into the parameters' existing
+    ``.grad`` buffers -- the views of the flat all-reduce bucket -- or returns them when no buffer is bound.
+
+    Preconditions (checked by the caller): only the four ft tensors require grad; x / x_weak do not."""
+
+    @staticmethod
+    def forward(ctx, cls_w, cls_b, box_w, box_b, x, xw, pack, spec, proposals, gt_boxes, gt_classes, weights, beta):
+        K1 = spec.K + 1
+        y1, y2 = predictor_gemm2(x, pack.W, pack.b, xw, pack.W[pack.o_vis:pack.o_vis + K1],
+                                 pack.b[pack.o_vis:pack.o_vis + K1])
+        delta, pd = y1[:, :K1], y1[:, K1:pack.o_ft]
+        ft_s, ft_d = y1[:, pack.o_ft:pack.o_ft + K1], y1[:, pack.o_ft + K1:pack.o_vis]
+        vis = y1[:, pack.o_vis:pack.o_vis + K1]
+        scores, bbox, _ = similarity_transfer_forward(spec, vis, delta, pd, y2[:, :K1], ft_s, ft_d, True, False, ())
+        losses, d_packed = fastrcnn_loss_packed(scores, bbox, proposals, gt_boxes, gt_classes, weights, beta)
+        ctx.save_for_backward(x, d_packed)
+        ctx.params = (cls_w, cls_b, box_w, box_b)
+        ctx.K1 = K1
+        ctx.n_cols = 5 * spec.K + 1
+        ctx.mark_non_differentiable(scores, bbox)
+        return losses[0], losses[1], scores, bbox
+
+    @staticmethod
+    def backward(ctx, g_cls, g_box, _gs, _gb):
+        x, d_packed = ctx.saved_tensors
+        cls_w, cls_b, box_w, box_b = ctx.params
+        params = (cls_w, cls_b, box_w, box_b)
+        need = ctx.needs_input_grad[:4]
+        bound = all((not n) or (p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == _F32)
+                    for p, n in zip(params, need))
+        if bound:  # accumulate in place (what autograd's AccumulateGrad would do with a returned tensor)
+            dst = [p.grad if n else None for p, n in zip(params, need)]
+            ret = (None, None, None, None)
+        else:
+            dst = [torch.empty_like(p) if n else None for p, n in zip(params, need)]
+            ret = tuple(dst)
+        sc = [_c(g_cls.reshape(1), _F32), _c(g_box.reshape(1), _F32)]
+        predictor_wgrad(d_packed, x, ctx.n_cols, [0, ctx.K1, ctx.n_cols], [dst[0], dst[2]], [dst[1], dst[3]], sc,
+                        accumulate=bound)
+        return ret + (None,) * 9
+
+
+def ft_step_losses(cls_w, cls_b, box_w, box_b, x, xw, pack, spec, proposals, gt_boxes, gt_classes,
+                   weights=(10.0, 10.0, 5.0, 5.0), beta=0.0):
+    """-> (loss_cls, loss_box_reg, scores [detached], bbox [detached])."""
+    return _FTStepLossFn.apply(cls_w, cls_b, box_w, box_b, x, xw, pack, spec, proposals, gt_boxes, gt_classes,
+                               tuple(weights), float(beta))
 
 
 # ------------------------------------------------------------------------------------------------- masks

@@ -48,13 +48,25 @@ class FusedSimilarity:
     ``S[R,Nn,B]`` on the fly.  ``materialize`` returns the explicit dict the reference's
     ``get_similarity_matrices`` returns (roi_heads.py:245-336)."""
 
-    def __init__(self, spec: ops.TransferSpec, vis_logits: Optional[torch.Tensor], heads: Sequence[str]):
+    def __init__(self, spec: ops.TransferSpec, vis_logits: Optional[torch.Tensor], heads: Sequence[str],
+                 feats: Optional[torch.Tensor] = None, weak_head=None):
         self.spec = spec
         self.vis_logits = vis_logits
         self.heads = tuple(heads)
+        # deferred form: the visual logits are mean-OICR(feats); the predictor computes them as extra columns of its
+        # packed GEMM when it is handed the same ``feats`` (predictors._packed_products), else ``ensure`` does
+        self.feats = feats
+        self.weak_head = weak_head
         self._cache: Optional[Dict[str, torch.Tensor]] = None
 
+    def ensure_vis_logits(self) -> Optional[torch.Tensor]:
+        if self.vis_logits is None and self.feats is not None:
+            with torch.no_grad():
+                self.vis_logits = self.weak_head.mean_logits(self.feats)
+        return self.vis_logits
+
     def materialize(self) -> Dict[str, torch.Tensor]:
+        self.ensure_vis_logits()
         if self._cache is None:
             R = self.vis_logits.shape[0] if self.vis_logits is not None else 1
             K = self.spec.K
@@ -352,6 +364,74 @@ class SupervisedDetectorOutputsBase(nn.Module):
         y = _linear(x, torch.cat(ws, 0), torch.cat(bs, 0), self.gemm_precision)
         return y[:, :K1], y[:, K1:K1 + K4], (y[:, K1 + K4:] if ft_c is not None else None)
 
+    # -- packed weights (one GEMM for every Linear of the predictor) ---------------------------------------------
+    class _Pack:
+        """W [rows, D] / b [rows]: rows [0, K1) cls_score_delta, [K1, o_ft) bbox_pred_delta, [o_ft, o_vis) the
+        fine-tune layers (when the predictor has them), [o_vis, o_vis + K1) the mean of the OICR refinement classifiers."""
+        __slots__ = ("W", "b", "o_ft", "o_vis", "key")
+
+    def _pack(self) -> "SupervisedDetectorOutputsBase._Pack":
+        """The persistent packed weight matrix.  Frozen blocks are copied in when their version changes; the TRAINABLE
+        fine-tune parameters are re-pointed at their rows (``param.data`` becomes a view of the pack), so the optimizer
+        updates the pack in place and no per-step concatenation is needed.  ``.to()`` / external ``.data`` swaps are
+        detected by pointer and the pack is rebuilt."""
+        K1, K4 = self.num_classes + 1, self.num_classes * self.box_dim
+        ft_c, ft_b = self._ft_layers()
+        ow, ob = self.weak_detector_head.mean_oicr_weight()
+        frozen = [self.cls_score_delta.weight, self.cls_score_delta.bias, self.bbox_pred_delta.weight,
+                  self.bbox_pred_delta.bias] + [q for p_ in self.weak_detector_head.oicr_predictors
+                                                for q in (p_.weight, p_.bias)]
+        dev = self.cls_score_delta.weight.device
+        o_ft = K1 + K4
+        o_vis = o_ft + (K1 + K4 if ft_c is not None else 0)
+        rows = o_vis + K1
+        key = (tuple(q._version for q in frozen), tuple(q.data_ptr() for q in frozen), str(dev), rows)
+        pk = self.__dict__.get("_wpack")
+        if pk is None or pk.key != key:
+            old = pk
+            pk = SupervisedDetectorOutputsBase._Pack()
+            D = self.input_size
+            pk.W = torch.zeros((rows, D), dtype=torch.float32, device=dev)
+            pk.b = torch.zeros((rows,), dtype=torch.float32, device=dev)
+            pk.o_ft, pk.o_vis, pk.key = o_ft, o_vis, key
+            with torch.no_grad():
+                pk.W[:K1].copy_(self.cls_score_delta.weight)
+                pk.W[K1:o_ft].copy_(self.bbox_pred_delta.weight)
+                pk.b[:K1].copy_(self.cls_score_delta.bias)
+                pk.b[K1:o_ft].copy_(self.bbox_pred_delta.bias)
+                pk.W[o_vis:].copy_(ow)
+                pk.b[o_vis:].copy_(ob)
+            self.__dict__["_wpack"] = pk
+            del old
+        if ft_c is not None:
+            es = pk.W.element_size()
+            want = ((ft_c.weight, pk.W[o_ft:o_ft + K1]), (ft_b.weight, pk.W[o_ft + K1:o_vis]),
+                    (ft_c.bias, pk.b[o_ft:o_ft + K1]), (ft_b.bias, pk.b[o_ft + K1:o_vis]))
+            for prm, view in want:
+                if prm.data_ptr() != view.data_ptr():
+                    with torch.no_grad():
+                        view.copy_(prm.data)
+                    prm.data = view
+            del es
+        return pk
+
+    def _can_pack(self, x: torch.Tensor) -> bool:
+        return (self.gemm_precision == "tf32" and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+                and x.shape[1] % 4 == 0 and self.weak_detector_head.oicr_iter > 0)
+
+    def _packed_products(self, x, x_weak_branch, similarity):
+        """Every Linear of an inference-mode forward as ONE grouped tcgen05 launch (+ one reduce): returns
+        (delta, proposal_deltas, ft_packed or None, weak_scores); fills ``similarity.vis_logits`` when it was deferred
+        on this same ``x``."""
+        pk = self._pack()
+        K1 = self.num_classes + 1
+        xw = x if x_weak_branch is None else x_weak_branch
+        y1, y2 = ops.predictor_gemm2(x, pk.W, pk.b, xw, pk.W[pk.o_vis:pk.o_vis + K1], pk.b[pk.o_vis:pk.o_vis + K1])
+        if isinstance(similarity, FusedSimilarity) and similarity.vis_logits is None and similarity.feats is x:
+            similarity.vis_logits = y1[:, pk.o_vis:pk.o_vis + K1]
+        ft = y1[:, pk.o_ft:pk.o_vis] if pk.o_vis > pk.o_ft else None
+        return y1[:, :K1], y1[:, K1:pk.o_ft], ft, y2[:, :K1]
+
     def _transfer_mode(self, similarity):
         """(do_transfer, novel_neg_inf, detach) for this predictor kind (fast_rcnn.py:401,427-428)."""
         return (similarity is not None and not self.training), self.training, False
@@ -363,10 +443,13 @@ class SupervisedDetectorOutputsBase(nn.Module):
             if self.training:
                 scores = scores.index_fill(1, novel_classes, float("-inf"))
             return [scores, bbox], self.weak_detector_head(x_weak)[0]
-        delta, pd, ft_packed = self._linears(x)
-        with torch.no_grad():
-            weak_scores = self.weak_detector_head.mean_logits(x if supervised_branch_x_weak is None
-                                                              else supervised_branch_x_weak)
+        if not torch.is_grad_enabled() and self._can_pack(x):  # inference: one grouped GEMM for all five products
+            delta, pd, ft_packed, weak_scores = self._packed_products(x, supervised_branch_x_weak, similarity)
+        else:
+            delta, pd, ft_packed = self._linears(x)
+            with torch.no_grad():
+                weak_scores = self.weak_detector_head.mean_logits(x if supervised_branch_x_weak is None
+                                                                  else supervised_branch_x_weak)
         do_transfer, neg_inf, detach = self._transfer_mode(similarity)
         spec, vis_logits = self._resolve_similarity(similarity, base_classes, novel_classes, x.device)
         scores, bbox = ops.similarity_transfer(spec, vis_logits, delta, pd, weak_scores, None, None, do_transfer,
@@ -378,7 +461,7 @@ class SupervisedDetectorOutputsBase(nn.Module):
 
     def _resolve_similarity(self, similarity, base_classes, novel_classes, dev):
         if isinstance(similarity, FusedSimilarity):
-            return similarity.spec, similarity.vis_logits
+            return similarity.spec, similarity.ensure_vis_logits()
         base, novel = base_classes.tolist(), novel_classes.tolist()
         if similarity is None:
             return self._plain_spec(base, novel, dev), None
@@ -482,6 +565,28 @@ class SupervisedDetectorOutputsFineTune(SupervisedDetectorOutputsBase):
 
     def _transfer_mode(self, similarity):
         return similarity is not None, False, False
+
+    def can_fuse_losses(self, x: torch.Tensor, x_weak_branch: Optional[torch.Tensor], spec: ops.TransferSpec) -> bool:
+        """True when the whole fine-tune step can run as the fused node ``ops.ft_step_losses``: the shipped fine-tune
+        setting -- only cls_score_ft / bbox_pred_ft train, the box-head features carry no gradient."""
+        trainable = [n for n, p_ in self.named_parameters() if p_.requires_grad]
+        only_ft = all(n.split(".")[0] in ("cls_score_ft", "bbox_pred_ft") for n in trainable) and len(trainable) == 4
+        return (self.training and torch.is_grad_enabled() and self._can_pack(x) and only_ft and not x.requires_grad
+                and (x_weak_branch is None or not x_weak_branch.requires_grad) and not getattr(spec, "wk", None)
+                and not spec.static_per_roi and self.box_reg_loss_type == "smooth_l1")
+
+    def forward_losses(self, x, x_weak_branch, spec: ops.TransferSpec, proposals):
+        """forward (fast_rcnn.py:484-533) + losses (:435-453) for sampled ``proposals`` as ONE autograd node.
+        Returns ({'loss_cls', 'loss_box_reg'}, [scores, bbox]) -- the predictions are detached."""
+        pk = self._pack()
+        gt_classes = layers.cat([p_.gt_classes for p_ in proposals])
+        prop = layers.cat([p_.proposal_boxes.tensor for p_ in proposals])
+        gt_boxes = layers.cat([p_.gt_boxes.tensor for p_ in proposals])
+        xw = x if x_weak_branch is None else x_weak_branch
+        loss_cls, loss_box, scores, bbox = ops.ft_step_losses(
+            self.cls_score_ft.weight, self.cls_score_ft.bias, self.bbox_pred_ft.weight, self.bbox_pred_ft.bias, x, xw, pk,
+            spec, prop, gt_boxes, gt_classes, self.box2box_transform.weights, self.smooth_l1_beta)
+        return {"loss_cls": loss_cls, "loss_box_reg": loss_box}, [scores, bbox]
 
 
 @FAST_RCNN_REGISTRY.register()

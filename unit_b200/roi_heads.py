@@ -345,6 +345,11 @@ class WSROIHead(StandardROIHeads):
             # head (COCO-*-ft.yaml, VOC 10-shot split 2/3) the loss reaches box_features through it.  Frozen features
             # (the usual fine-tune setting, and inference) skip the graph.
             track = torch.is_grad_enabled() and feats.requires_grad
+            defer = (not track and not spec.wk and not return_similarity and not torch.is_grad_enabled()
+                     and getattr(self.box_predictor, "_can_pack", lambda t: False)(feats))
+            if defer:  # inference: the predictor's packed GEMM produces these columns (predictors._packed_products)
+                return FusedSimilarity(spec, None, tuple(self.terms.keys()), feats=feats,
+                                       weak_head=self.box_predictor.weak_detector_head)
             with torch.set_grad_enabled(track):
                 vis_logits = self.box_predictor.weak_detector_head.mean_logits(feats)
             with torch.no_grad():
@@ -357,6 +362,21 @@ class WSROIHead(StandardROIHeads):
             viz = None if vis_logits is None else vis_logits.index_select(1, self._base_classes_tensor)
             return sim, [raw, viz]
         return sim
+
+    def box_losses(self, x: torch.Tensor, weak_branch: Optional[torch.Tensor], proposals: List[Instances]):
+        """Similarity -> predictor -> losses for sampled proposals (the training half of roi_heads.py:618-624).  The
+        shipped fine-tune setting (only cls_score_ft / bbox_pred_ft train, frozen box head) runs as ONE fused autograd
+        node; everything else takes the modular path.  Returns (losses dict, similarity or None)."""
+        pred = self.box_predictor
+        spec = self._transfer_spec(x.device)
+        if getattr(pred, "can_fuse_losses", None) is not None and pred.can_fuse_losses(x, weak_branch, spec):
+            losses, _ = pred.forward_losses(x, weak_branch, spec, proposals)
+            return losses, None
+        # base training applies no transfer (roi_heads.py:519-521): the similarity is only built by the *FineTune heads
+        similarity = self.get_similarity_matrices(x) if getattr(self, "ALWAYS_TRANSFER", False) else None
+        predictions, _ = pred(x, supervised_branch_x_weak=weak_branch, novel_classes=self._novel_classes_tensor,
+                              base_classes=self._base_classes_tensor, similarity=similarity)
+        return pred.losses(predictions, proposals), similarity
 
     # -- shared forward pieces -----------------------------------------------------------------------------
     def _truncate_weak(self, weak_proposals):
@@ -406,6 +426,10 @@ class WSROIHeadNoMeta(WSROIHead):
             _, box_features, weak_branch = self._box_features(features, proposals)
             x = box_features.mean(dim=[2, 3]) if box_features.dim() > 2 else box_features
         similarity, sim_values = None, None
+        if (self.training and self.ALWAYS_TRANSFER and x is not None and x_weak is None and not self.train_on_pred_boxes
+                and not return_similarity):
+            losses, similarity = self.box_losses(x, weak_branch, proposals)  # fused when the setting allows it
+            return losses, box_features, similarity
         if self.ALWAYS_TRANSFER or not self.training:
             if return_similarity:
                 similarity, sim_values = self.get_similarity_matrices(box_features, return_similarity=True)

@@ -133,10 +133,7 @@ class RoIStage:
         pooled = ops.roi_align_forward(features, rois, pool.output_size, pool.scales[0], pool.sampling_ratio,
                                        pool.aligned, True)
         x, xw = self.box_head_fn(pooled)
-        sim = head.get_similarity_matrices(x)
-        predictions, _ = head.box_predictor(x, supervised_branch_x_weak=xw, novel_classes=head._novel_classes_tensor,
-                                            base_classes=head._base_classes_tensor, similarity=sim)
-        losses = head.box_predictor.losses(predictions, sampled)
+        losses, _ = head.box_losses(x, xw, sampled)  # ONE fused node in the shipped fine-tune setting
         loss = losses["loss_cls"] + losses["loss_box_reg"]
         loss.backward()
         return loss.detach(), rois, pooled
