@@ -268,3 +268,79 @@ def test_product_never_imports_oracle():
     for f in glob.glob(os.path.join(ROOT, "unit_b200", "*.py")):
         src = open(f).read()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_custom_ops_registered_with_fake_and_autograd():
+    """north_star: 'a thin C-ABI torch custom-op layer'.  Every op of unit_b200.torch_ops is a torch.library custom op
+    with a fake (meta) implementation; the differentiable ones have an autograd formula registered."""
+    import torch
+    from unit_b200 import ops, torch_ops  # noqa: F401
+
+    for name in torch_ops.OP_NAMES:
+        packet = getattr(torch.ops.unit_b200, name)
+        assert packet.default._schema.name == f"unit_b200::{name}"
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    with FakeTensorMode():
+        feat = torch.empty(2, 64, 50, 84, device="cuda", requires_grad=True)
+        rois = torch.empty(96, 5, device="cuda")
+        out = ops.roi_align(feat, rois, 14, 1 / 16, 0, True, rois_sorted=True)
+        assert out.shape == (96, 64, 14, 14) and out.device.type == "cuda"
+        # an autograd formula is registered: the output carries a grad_fn (running the engine on a CUDA device needs a
+        # GPU, so the backward itself is exercised by opcheck on the GPU box: tests/test_ops_gpu.py::test_opcheck)
+        assert out.requires_grad and out.grad_fn is not None
+        g = ops.roi_align_backward(torch.empty_like(out), rois, feat.shape, 1 / 16, 0, True, True)
+        assert g.shape == feat.shape
+        x = torch.empty(128, 256, device="cuda")
+        w = torch.empty(40, 256, device="cuda", requires_grad=True)
+        b = torch.empty(40, device="cuda", requires_grad=True)
+        y = ops.linear_tf32(x, w, b)
+        assert y.shape == (128, 40) and y.grad_fn is not None
+        gw, gb = torch.ops.unit_b200.predictor_wgrad(torch.empty(128, 40, device="cuda"), x)
+        assert gw.shape == w.shape and gb.shape == b.shape
+
+
+def test_heads_trace_under_fake_tensor():
+    """The device half of inference (ROIPooler -> packed predictor GEMM -> fused similarity + transfer -> softmax +
+    decode -> filter + NMS + top-k) runs under FakeTensorMode on a box without a GPU: only shapes flow, every kernel
+    call is a torch.ops.unit_b200 op with a registered fake implementation."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    from unit_b200 import d2compat  # noqa: F401
+    from unit_b200.config import load_cfg
+    from unit_b200.registry import ROI_BOX_HEAD_REGISTRY
+    from unit_b200.roi_heads import build_roi_heads
+    from unit_b200.structures import Boxes, Instances, ShapeSpec
+
+    class _Feat(torch.nn.Module):
+        def __init__(self, cfg, input_shape):
+            super().__init__()
+
+        @property
+        def output_shape(self):
+            return ShapeSpec(channels=256, height=1, width=1)
+
+    if "FakeTraceHead" not in ROI_BOX_HEAD_REGISTRY:
+        ROI_BOX_HEAD_REGISTRY._do_register("FakeTraceHead", _Feat)
+    cfg = load_cfg(os.path.join(ROOT, "configs", "voc_split1_ft.yaml"),
+                   ["MODEL.ROI_BOX_HEAD.NAME", "FakeTraceHead", "MODEL.ROI_HEADS.EMBEDDING_PATH",
+                    os.path.join(ROOT, "tests", "golden", "glove_mean.pt")])
+    with FakeTensorMode(allow_non_fake_inputs=True), torch.device("cuda"):
+        head = build_roi_heads(cfg, {"res4": ShapeSpec(channels=64, stride=16)}).eval()  # parameters: fake CUDA tensors
+        emb = head.box_predictor.embeddings  # loaded from disk (a real CPU tensor): stand in a fake CUDA one
+        emb.weight = torch.nn.Parameter(torch.empty(tuple(emb.weight.shape), device="cuda"), requires_grad=False)
+        feats = torch.empty(2, 64, 50, 84, device="cuda")
+        props = [Instances((800, 1333), proposal_boxes=Boxes(torch.empty(300, 4, device="cuda")),
+                           objectness_logits=torch.empty(300, device="cuda")) for _ in range(2)]
+        with torch.no_grad():
+            head.move_mappings_to_gpu()
+            pooled = head.box_pooler([feats], [p.proposal_boxes for p in props])
+            assert pooled.shape == (600, 64, 14, 14)
+            x = torch.empty(600, 256, device="cuda")
+            sim = head.get_similarity_matrices(x)
+            predictions, _ = head.box_predictor(x, supervised_branch_x_weak=x, novel_classes=head._novel_classes_tensor,
+                                                base_classes=head._base_classes_tensor, similarity=sim)
+            assert predictions[0].shape == (600, 21) and predictions[1].shape == (600, 80)
+            db, ds, dc, dr, cnt = head.box_predictor.inference_device(predictions, props)
+            assert db.shape == (2, 100, 4) and ds.shape == (2, 100) and cnt.shape == (2,)

@@ -259,9 +259,9 @@ static void plan(int M, int N, int K, Params* p) {
 // dW[N, K] = gy[R, N]^T . x[R, K]   (contraction over the R RoIs; N = trainable predictor columns <= 128, K = 2048)
 // Both operands are consumed exactly as they lie in memory -- row-major with the CONTRACTED index (the RoI) as the row
 // -- i.e. as MN-major UMMA operands: a TMA box {32 floats, KR rows, blocks} of the 3-D view (col, row, col / 32) lands
-// as [block][row][32 floats] with the 128-byte swizzle, the canonical MN-major SW128 layout (8-row groups 1024 B apart
-// = SBO, 32-column blocks KR * 128 B apart = LBO).  One tcgen05.mma (M = 128 classes, N = 256 features, K = 8 RoIs)
-// per 8 rows; grid = (K / 256 feature tiles) x (R / 128 RoI splits); partials are summed in a fixed order by
+// as [block][row][32 floats] with the 128-byte / 32-byte-atom swizzle, the canonical MN-major layout for 32-bit
+// operands (4-row groups 512 B apart = SBO, 32-column blocks KR * 128 B apart = LBO).  One tcgen05.mma (M = 128
+// classes, N = 256 features, K = 8 RoIs) per 8 rows; grid = (K / 256 feature tiles) x (R / 128 RoI splits); partials are summed in a fixed order by
 // wgrad_reduce_kernel, which also scales the rows (dL/dloss), adds the bias column sums and writes -- or accumulates
 // -- straight into the parameter-gradient buffers (the flat NCCL bucket).
 constexpr int WG_KR = 32;      // RoI rows per stage
@@ -277,14 +277,17 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-// MN-major operand tile, 128-byte swizzle: LBO = bytes between 32-column blocks, SBO = 1024 (8 rows x 128 B)
+// MN-major operand tile of 32-bit elements.  The only shared-memory layout UMMA accepts for MN-major TF32 operands is
+// the 128-byte swizzle with a 32-byte base (layout type 1): rows of 128 B (32 floats along M/N), atoms of FOUR K-rows
+// (512 B) inside which the 32-byte chunk index is XORed with the row index -- what TMA writes with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  LBO = bytes between 32-column blocks, SBO = 512 (4 rows x 128 B).
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(512 >> 4) << 32;
   d |= (uint64_t)1 << 46;  // version = 1
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -345,7 +348,7 @@ tf32_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_consta
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_addr = smem_u32(sa + s * a_bytes), b_addr = smem_u32(sb + s * b_bytes);
 #pragma unroll
-      for (int k = 0; k < WG_KR / UK; ++k) {  // 8 RoI rows per MMA: one 1024-byte swizzle atom down every block
+      for (int k = 0; k < WG_KR / UK; ++k) {  // 8 RoI rows per MMA: two 512-byte swizzle atoms down every block
         const uint64_t da = make_desc_mn(a_addr + k * 1024, WG_KR * 128), db = make_desc_mn(b_addr + k * 1024, WG_KR * 128);
         const uint32_t accumulate = (s > 0 || k > 0) ? 1u : 0u;
         asm volatile(
@@ -451,7 +454,7 @@ static int make_map_mn(CUtensorMap* map, const float* ptr, int rows, int cols, i
   cuuint32_t box[3] = {32, (cuuint32_t)WG_KR, (cuuint32_t)box_blocks};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   UNIT_REQUIRE(r == CUDA_SUCCESS, "predictor_wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r);
   return UNIT_OK;

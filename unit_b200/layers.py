@@ -23,7 +23,7 @@ def _adjacent_rows(tensors: List[torch.Tensor]) -> Optional[torch.Tensor]:
     """The tensors as ONE view when they are consecutive row blocks of the same buffer (the per-image slices of a
     flat kernel output, e.g. what ``sample_from_draw`` hands out), else None."""
     first = tensors[0]
-    if first.requires_grad or not first.is_contiguous() or first.dim() == 0:
+    if first.requires_grad or not first.is_contiguous() or first.dim() == 0 or ops._is_fake(first):
         return None
     base, rest = first.untyped_storage().data_ptr(), first.shape[1:]
     nxt, rows = first.storage_offset(), 0

@@ -53,6 +53,11 @@ def _c(t: torch.Tensor, dtype=None) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _is_fake(t: torch.Tensor) -> bool:
+    from torch._subclasses.fake_tensor import FakeTensor
+    return isinstance(t, FakeTensor)
+
+
 _WS = {}
 
 
@@ -77,7 +82,8 @@ def _i32(values: Sequence[int], dev: torch.device) -> torch.Tensor:
         if len(_I32_CACHE) >= 512:
             _I32_CACHE.clear()
         t = torch.tensor(list(key[0]), dtype=torch.int32, device=dev)
-        _I32_CACHE[key] = t
+        if not _is_fake(t):  # tracing under FakeTensorMode must not poison the cache of real constants
+            _I32_CACHE[key] = t
     return t
 
 
@@ -92,7 +98,8 @@ def f32_const(values: Sequence[Sequence[float]], dev: torch.device) -> torch.Ten
         if len(_F32_CACHE) >= 512:
             _F32_CACHE.clear()
         t = torch.tensor([list(r) for r in key[0]], dtype=torch.float32, device=dev)
-        _F32_CACHE[key] = t
+        if not _is_fake(t):
+            _F32_CACHE[key] = t
     return t
 
 
@@ -105,7 +112,9 @@ def _ones(n: int, dev: torch.device) -> torch.Tensor:
     if t is None:
         if len(_ONES_CACHE) >= 64:
             _ONES_CACHE.clear()
-        t = _ONES_CACHE[key] = torch.ones(int(n), dtype=torch.float32, device=dev)
+        t = torch.ones(int(n), dtype=torch.float32, device=dev)
+        if not _is_fake(t):
+            _ONES_CACHE[key] = t
     return t
 
 
@@ -125,7 +134,7 @@ def _dtype_code(t: torch.Tensor) -> int:
     raise RuntimeError(f"roi_align: unsupported dtype {t.dtype} (f32 and bf16 only)")
 
 
-def boxes_to_rois(boxes: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+def _boxes_to_rois_impl(boxes: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
     """[D2] convert_boxes_to_pooler_format in one launch: [R,4] boxes in image order + int32 offsets -> [R,5] rois."""
     dev = _need_cuda(boxes, offsets)
     boxes = _c(boxes, _F32)
@@ -136,7 +145,7 @@ def boxes_to_rois(boxes: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
     return rois
 
 
-def roi_align_forward(feat: torch.Tensor, rois: torch.Tensor, output_size: Tuple[int, int], spatial_scale: float,
+def _roi_align_forward_impl(feat: torch.Tensor, rois: torch.Tensor, output_size: Tuple[int, int], spatial_scale: float,
                       sampling_ratio: int, aligned: bool, rois_sorted: bool) -> torch.Tensor:
     dev = _need_cuda(feat, rois)
     feat = _c(feat)
@@ -155,7 +164,7 @@ def roi_align_forward(feat: torch.Tensor, rois: torch.Tensor, output_size: Tuple
     return out
 
 
-def roi_align_backward(grad_out: torch.Tensor, rois: torch.Tensor, input_shape: Sequence[int], spatial_scale: float,
+def _roi_align_backward_impl(grad_out: torch.Tensor, rois: torch.Tensor, input_shape: Sequence[int], spatial_scale: float,
                        sampling_ratio: int, aligned: bool, rois_sorted: bool) -> torch.Tensor:
     dev = _need_cuda(grad_out, rois)
     grad_out = _c(grad_out)
@@ -172,27 +181,31 @@ def roi_align_backward(grad_out: torch.Tensor, rois: torch.Tensor, input_shape: 
     return grad_in
 
 
-class _ROIAlignFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, feat, rois, output_size, spatial_scale, sampling_ratio, aligned, rois_sorted):
-        ctx.save_for_backward(rois)
-        ctx.cfg = (tuple(feat.shape), spatial_scale, sampling_ratio, aligned, rois_sorted)
-        return roi_align_forward(feat, rois, output_size, spatial_scale, sampling_ratio, aligned, rois_sorted)
+def boxes_to_rois(boxes: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    """[D2] convert_boxes_to_pooler_format in one launch (torch.ops.unit_b200.boxes_to_rois)."""
+    return torch.ops.unit_b200.boxes_to_rois(boxes, offsets)
 
-    @staticmethod
-    def backward(ctx, grad_out):
-        (rois,) = ctx.saved_tensors
-        shape, scale, sr, aligned, srt = ctx.cfg
-        return roi_align_backward(grad_out, rois, shape, scale, sr, aligned, srt), None, None, None, None, None, None
+
+def roi_align_forward(feat: torch.Tensor, rois: torch.Tensor, output_size: Tuple[int, int], spatial_scale: float,
+                      sampling_ratio: int, aligned: bool, rois_sorted: bool) -> torch.Tensor:
+    return torch.ops.unit_b200.roi_align(feat, rois, int(output_size[0]), int(output_size[1]), float(spatial_scale),
+                                         int(sampling_ratio), bool(aligned), bool(rois_sorted))
+
+
+def roi_align_backward(grad_out: torch.Tensor, rois: torch.Tensor, input_shape: Sequence[int], spatial_scale: float,
+                       sampling_ratio: int, aligned: bool, rois_sorted: bool) -> torch.Tensor:
+    n, c, h, w = [int(v) for v in input_shape]
+    return torch.ops.unit_b200.roi_align_backward(grad_out, rois, n, c, h, w, float(spatial_scale), int(sampling_ratio),
+                                                  bool(aligned), bool(rois_sorted))
 
 
 def roi_align(feat: torch.Tensor, rois: torch.Tensor, output_size, spatial_scale: float = 1.0,
               sampling_ratio: int = 0, aligned: bool = True, rois_sorted: bool = False) -> torch.Tensor:
-    """[TV] torchvision.ops.roi_align / [D2] ROIAlign drop-in (rois: [R,5] batch_idx,x1,y1,x2,y2)."""
+    """[TV] torchvision.ops.roi_align / [D2] ROIAlign drop-in (rois: [R,5] batch_idx,x1,y1,x2,y2); differentiable
+    w.r.t. ``feat`` (torch.ops.unit_b200.roi_align, backward = torch.ops.unit_b200.roi_align_backward)."""
     if isinstance(output_size, int):
         output_size = (output_size, output_size)
-    return _ROIAlignFn.apply(feat, rois, tuple(output_size), float(spatial_scale), int(sampling_ratio), bool(aligned),
-                             bool(rois_sorted))
+    return roi_align_forward(feat, rois, tuple(output_size), spatial_scale, sampling_ratio, aligned, rois_sorted)
 
 
 # ------------------------------------------------------------------------------------------------- IoU / matcher
@@ -230,7 +243,7 @@ def matcher(iou: torch.Tensor, thresholds: Sequence[float], labels: Sequence[int
     return (matches, mlabels, vals) if want_vals else (matches, mlabels)
 
 
-def iou_match(gt_boxes: torch.Tensor, gt_offsets: torch.Tensor, prop_boxes: torch.Tensor, prop_offsets: torch.Tensor,
+def _iou_match_impl(gt_boxes: torch.Tensor, gt_offsets: torch.Tensor, prop_boxes: torch.Tensor, prop_offsets: torch.Tensor,
               thresholds: Sequence[float], labels: Sequence[int], want_vals: bool = True):
     """Fused pairwise_iou + Matcher for all images (offsets: int32 [n_img+1] on device)."""
     dev = _need_cuda(prop_boxes, prop_offsets, gt_offsets)
@@ -244,6 +257,14 @@ def iou_match(gt_boxes: torch.Tensor, gt_offsets: torch.Tensor, prop_boxes: torc
     check(lib().unit_iou_match(_ptr(gt_boxes), _ptr(gt_offsets), _ptr(prop_boxes), _ptr(prop_offsets), n_img, Pt, thr,
                                lab, T, _ptr(matches), _ptr(mlabels), _ptr(vals), _stream()), "unit_iou_match")
     return matches, mlabels, vals
+
+
+def iou_match(gt_boxes: torch.Tensor, gt_offsets: torch.Tensor, prop_boxes: torch.Tensor, prop_offsets: torch.Tensor,
+              thresholds: Sequence[float], labels: Sequence[int], want_vals: bool = True):
+    """Fused pairwise_iou + Matcher for all images (torch.ops.unit_b200.iou_match)."""
+    m, l, v = torch.ops.unit_b200.iou_match(gt_boxes, gt_offsets, prop_boxes, prop_offsets,
+                                            [float(t) for t in thresholds], [int(x) for x in labels])
+    return m, l, (v if want_vals else None)
 
 
 def label_proposals(matches, mlabels, gt_classes, gt_offsets, prop_offsets, num_classes: int):
@@ -284,7 +305,7 @@ def sample_gather(pos_idx, neg_idx, perm_pos, perm_pos_off, perm_neg, perm_neg_o
 SCALE_CLAMP = math.log(1000.0 / 16)
 
 
-def softmax_decode(scores: Optional[torch.Tensor], deltas: Optional[torch.Tensor], proposals: Optional[torch.Tensor],
+def _softmax_decode_impl(scores: Optional[torch.Tensor], deltas: Optional[torch.Tensor], proposals: Optional[torch.Tensor],
                    weights=(10.0, 10.0, 5.0, 5.0), scale_clamp: float = SCALE_CLAMP, want_probs=True, want_boxes=True):
     dev = _need_cuda(scores, deltas)
     R = (scores if scores is not None else deltas).shape[0]
@@ -304,6 +325,15 @@ def softmax_decode(scores: Optional[torch.Tensor], deltas: Optional[torch.Tensor
                                         float(weights[0]), float(weights[1]), float(weights[2]), float(weights[3]),
                                         float(scale_clamp), _stream()), "unit_softmax_decode")
     return probs, boxes
+
+
+def softmax_decode(scores: Optional[torch.Tensor], deltas: Optional[torch.Tensor], proposals: Optional[torch.Tensor],
+                   weights=(10.0, 10.0, 5.0, 5.0), scale_clamp: float = SCALE_CLAMP, want_probs=True, want_boxes=True):
+    """softmax and / or Box2BoxTransform.apply_deltas in one launch (torch.ops.unit_b200.softmax_decode)."""
+    probs, boxes = torch.ops.unit_b200.softmax_decode(scores if want_probs else None, deltas if want_boxes else None,
+                                                      proposals if want_boxes else None, [float(w) for w in weights],
+                                                      float(scale_clamp))
+    return (probs if want_probs else None), (boxes if want_boxes else None)
 
 
 def box_get_deltas(src: torch.Tensor, tgt: torch.Tensor, weights=(10.0, 10.0, 5.0, 5.0)) -> torch.Tensor:
@@ -433,7 +463,7 @@ def weighted_ce_loss(scores, labels, weights):
 NMS_CLASSWISE, NMS_COORD_TRICK, NMS_TV_CUDA_RULE, NMS_TV_CPU_RULE = 0, 1, 2, 3
 
 
-def detect(boxes: torch.Tensor, probs: torch.Tensor, roi_offsets: torch.Tensor, image_hw: torch.Tensor,
+def _detect_impl(boxes: torch.Tensor, probs: torch.Tensor, roi_offsets: torch.Tensor, image_hw: torch.Tensor,
            score_thresh: float, nms_thresh: float, topk: int, nms_mode: int = NMS_TV_CUDA_RULE):
     """fast_rcnn_inference for a batch: returns det_boxes [n,topk,4], det_scores [n,topk], det_classes i64,
     det_roi i64 (index into the image's finite rows), det_counts i32 [n] -- all on device, no sync."""
@@ -469,6 +499,15 @@ def detect(boxes: torch.Tensor, probs: torch.Tensor, roi_offsets: torch.Tensor, 
                                                                       cand_counts)
 
 
+def detect(boxes: torch.Tensor, probs: torch.Tensor, roi_offsets: torch.Tensor, image_hw: torch.Tensor,
+           score_thresh: float, nms_thresh: float, topk: int, nms_mode: int = NMS_TV_CUDA_RULE):
+    """fast_rcnn_inference for a batch (torch.ops.unit_b200.detect): det_boxes [n,topk,4], det_scores, det_classes,
+    det_roi, det_counts, (candidates) -- all on device, no sync."""
+    o = torch.ops.unit_b200.detect(boxes, probs, roi_offsets, image_hw, float(score_thresh), float(nms_thresh),
+                                   int(topk), int(nms_mode))
+    return o[0], o[1], o[2], o[3], o[4], tuple(o[5:])
+
+
 def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: Optional[torch.Tensor], iou_threshold: float,
                 nms_mode: int = NMS_TV_CUDA_RULE, max_keep: int = -1) -> torch.Tensor:
     """[TV] torchvision.ops.batched_nms (idxs given) / nms (idxs None) drop-in: int64 indices, score-descending."""
@@ -494,7 +533,7 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torc
 
 
 # ------------------------------------------------------------------------------------------------- transfer
-def lingual_similarity(emb: torch.Tensor, indexer: torch.Tensor, base: torch.Tensor, novel: torch.Tensor):
+def _lingual_similarity_impl(emb: torch.Tensor, indexer: torch.Tensor, base: torch.Tensor, novel: torch.Tensor):
     """fast_rcnn.py:376-382 -> (raw [Nn,B], softmax(raw, -1))."""
     dev = _need_cuda(emb)
     emb = _c(emb, _F32)
@@ -505,6 +544,11 @@ def lingual_similarity(emb: torch.Tensor, indexer: torch.Tensor, base: torch.Ten
     check(lib().unit_lingual_similarity(_ptr(emb), _ptr(indexer), _ptr(base), _ptr(novel), emb.shape[1], B, Nn,
                                         _ptr(raw), _ptr(soft), _stream()), "unit_lingual_similarity")
     return raw, soft
+
+
+def lingual_similarity(emb: torch.Tensor, indexer: torch.Tensor, base: torch.Tensor, novel: torch.Tensor):
+    """fast_rcnn.py:376-382 -> (raw [Nn,B], softmax(raw, -1))  (torch.ops.unit_b200.lingual_similarity)."""
+    return torch.ops.unit_b200.lingual_similarity(emb, indexer, base, novel)
 
 
 def make_class_kind(num_classes: int, base: Sequence[int], novel: Sequence[int], dev) -> torch.Tensor:
@@ -533,6 +577,19 @@ class TransferSpec:
         self.static_per_roi = int(static_per_roi)
         self.wk = {}
 
+    @classmethod
+    def from_tensors(cls, num_classes: int, base_i32, novel_i32, class_kind, static: dict, wv: Sequence[float],
+                     norm: Sequence[int], vis_threshold: float, static_per_roi: int) -> "TransferSpec":
+        """Rebuild a spec from the flat arguments of torch.ops.unit_b200.similarity_transfer."""
+        self = cls.__new__(cls)
+        self.K, self.B, self.Nn = int(num_classes), int(base_i32.numel()), int(novel_i32.numel())
+        self.base_i32, self.novel_i32, self.class_kind = base_i32, novel_i32, class_kind
+        self.static = dict(static)
+        self.wv = dict(zip(("cls", "bbox", "seg"), wv))
+        self.norm = dict(zip(("cls", "bbox", "seg"), norm))
+        self.vis_threshold, self.static_per_roi, self.wk = float(vis_threshold), int(static_per_roi), {}
+        return self
+
     def with_static(self, static: dict, static_per_roi: int) -> "TransferSpec":
         """Same class sets and term weights with other static blocks (per-RoI terms: bit h of ``static_per_roi``)."""
         import copy
@@ -550,7 +607,7 @@ class TransferSpec:
                               int(do_transfer), int(novel_neg_inf), self.static_per_roi)
 
 
-def similarity_transfer_forward(spec: TransferSpec, vis_logits, delta_scores, proposal_deltas, weak_scores=None,
+def _similarity_transfer_forward_impl(spec: TransferSpec, vis_logits, delta_scores, proposal_deltas, weak_scores=None,
                                 ft_scores=None, ft_deltas=None, do_transfer=True, novel_neg_inf=False,
                                 want_similarity: Sequence[str] = ()):
     dev = _need_cuda(delta_scores, proposal_deltas)
@@ -582,6 +639,22 @@ def similarity_transfer_forward(spec: TransferSpec, vis_logits, delta_scores, pr
                                              _ptr(sims["cls"]), _ptr(sims["bbox"]), _ptr(sims["seg"]), _stream()),
               "unit_similarity_transfer")
     return out_scores, out_bbox, sims
+
+
+def similarity_transfer_forward(spec: TransferSpec, vis_logits, delta_scores, proposal_deltas, weak_scores=None,
+                                ft_scores=None, ft_deltas=None, do_transfer=True, novel_neg_inf=False,
+                                want_similarity: Sequence[str] = ()):
+    """Fused similarity + transfer (torch.ops.unit_b200.similarity_transfer) -> (scores, bbox, {head: S or None})."""
+    g = lambda d, k: d.get(k, 0)
+    want = sum(1 << i for i, h in enumerate(("cls", "bbox", "seg")) if h in want_similarity)
+    s_, b_, sc, sb, ss = torch.ops.unit_b200.similarity_transfer(
+        vis_logits, spec.static.get("cls"), spec.static.get("bbox"), spec.static.get("seg"), spec.base_i32,
+        spec.novel_i32, spec.class_kind, delta_scores, proposal_deltas, weak_scores, ft_scores, ft_deltas,
+        float(spec.vis_threshold), [float(g(spec.wv, h)) for h in ("cls", "bbox", "seg")],
+        [int(g(spec.norm, h)) for h in ("cls", "bbox", "seg")], bool(do_transfer), bool(novel_neg_inf),
+        int(spec.static_per_roi), want)
+    pick = lambda t, i: t if (want >> i) & 1 else None
+    return s_, b_, {"cls": pick(sc, 0), "bbox": pick(sb, 1), "seg": pick(ss, 2)}
 
 
 def similarity_transfer_backward(spec: TransferSpec, s_cls, s_bbox, g_scores, g_bbox, detach_transfer=False):
@@ -697,7 +770,7 @@ def similarity_transfer(spec: TransferSpec, vis_logits, delta_scores, proposal_d
 
 
 # ------------------------------------------------------------------------------------------------- predictor GEMM
-def predictor_gemm_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+def _predictor_gemm_forward_impl(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
     """y = x @ w.T + bias on the tcgen05 tensor cores (TF32 multiply, fp32 accumulate in TMEM)."""
     dev = _need_cuda(x, w)
     x, w = _c(x, _F32), _c(w, _F32)
@@ -714,37 +787,19 @@ def predictor_gemm_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torc
     return y
 
 
-class _LinearTF32Fn(torch.autograd.Function):
-    """Forward on the hand-written tcgen05 GEMM; the weight/bias gradients are plain library GEMMs (cuBLAS, TF32)."""
-
-    @staticmethod
-    def forward(ctx, x, w, bias):
-        ctx.save_for_backward(x, w)
-        ctx.has_bias = bias is not None
-        return predictor_gemm_forward(x, w, bias)
-
-    @staticmethod
-    def backward(ctx, gy):
-        x, w = ctx.saved_tensors
-        # same precision contract as the forward (TF32 multiply, fp32 accumulate; north_star: transfer rel 1e-2)
-        old = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-        try:
-            gx = gy @ w if ctx.needs_input_grad[0] else None
-            gw = gy.t() @ x if ctx.needs_input_grad[1] else None
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = old
-        gb = None
-        if ctx.has_bias and ctx.needs_input_grad[2]:  # column sums as one fp32 gemv instead of a strided reduction
-            gb = torch.mv(gy.t(), _ones(gy.shape[0], gy.device))
-        return gx, gw, gb
+def predictor_gemm_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """y = x @ w.T + bias on the tcgen05 tensor cores (torch.ops.unit_b200.predictor_linear)."""
+    return torch.ops.unit_b200.predictor_linear(x, w, bias)
 
 
 def linear_tf32(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    return _LinearTF32Fn.apply(x, w, bias)
+    """Differentiable predictor Linear: forward and weight / bias gradients on the hand-written tcgen05 kernels
+    (torch.ops.unit_b200.predictor_linear / predictor_wgrad); only d/dx -- unused on the fine-tune path -- is a
+    library GEMM."""
+    return torch.ops.unit_b200.predictor_linear(x, w, bias)
 
 
-def predictor_gemm2(x1: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], x2: Optional[torch.Tensor] = None,
+def _predictor_gemm2_impl(x1: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], x2: Optional[torch.Tensor] = None,
                     w2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None):
     """Two products sharing M and K in ONE tcgen05 launch (+ one reduce launch):
     y1 = x1 @ w1.T + b1 and y2 = x2 @ w2.T + b2.  Output rows are padded to a multiple of 32 columns (zeros), so
@@ -769,6 +824,14 @@ def predictor_gemm2(x1: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tenso
     check(lib().unit_predictor_gemm2(_ptr(x1), _ptr(w1), _ptr(b1), _ptr(y1), N1, ld1, _ptr(x2), _ptr(w2), _ptr(b2),
                                      _ptr(y2), N2, ld2, M, K, _ptr(ws), ws.numel(), _stream()), "unit_predictor_gemm2")
     return y1, y2
+
+
+def predictor_gemm2(x1: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], x2: Optional[torch.Tensor] = None,
+                    w2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None):
+    """Two products sharing M and K in one launch (torch.ops.unit_b200.predictor_gemm2); see the implementation."""
+    if x2 is None:
+        return _predictor_gemm2_impl(x1, w1, b1)
+    return torch.ops.unit_b200.predictor_gemm2(x1, w1, b1, x2, w2, b2)
 
 
 def predictor_wgrad(gy: torch.Tensor, x: torch.Tensor, n_cols: int, seg_rows: Sequence[int],
@@ -899,7 +962,7 @@ def mask_transfer(logits: torch.Tensor, s_seg: Optional[torch.Tensor], spec: Tra
     return out_logits, out_probs
 
 
-def mask_paste(masks: torch.Tensor, boxes: torch.Tensor, image_shape: Tuple[int, int], threshold: float = 0.5):
+def _mask_paste_impl(masks: torch.Tensor, boxes: torch.Tensor, image_shape: Tuple[int, int], threshold: float = 0.5):
     """[D2] paste_masks_in_image: masks [D,M,M] -> bool [D,H,W]."""
     dev = _need_cuda(masks, boxes)
     masks, boxes = _c(masks, _F32), _c(boxes, _F32)
@@ -910,3 +973,11 @@ def mask_paste(masks: torch.Tensor, boxes: torch.Tensor, image_shape: Tuple[int,
         check(lib().unit_mask_paste(_ptr(masks), _ptr(boxes), D, M, h, w, float(threshold), _ptr(out), _stream()),
               "unit_mask_paste")
     return out.view(torch.bool)
+
+
+def mask_paste(masks: torch.Tensor, boxes: torch.Tensor, image_shape: Tuple[int, int], threshold: float = 0.5):
+    """[D2] paste_masks_in_image (torch.ops.unit_b200.mask_paste): masks [D,M,M] -> bool [D,H,W]."""
+    return torch.ops.unit_b200.mask_paste(masks, boxes, int(image_shape[0]), int(image_shape[1]), float(threshold))
+
+
+from . import torch_ops as _torch_ops  # noqa: E402,F401  (registers torch.ops.unit_b200.* on top of the *_impl functions)

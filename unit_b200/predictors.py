@@ -153,7 +153,8 @@ class WeakDetectorOutputsBase(nn.Module):
         """mean_k(W_k x + b_k) == (mean_k W_k) x + mean_k b_k: the 3 refinement classifiers collapse to one."""
         params = [q for p in self.oicr_predictors for q in (p.weight, p.bias)]
         frozen = not any(q.requires_grad for q in params)
-        key = (tuple(q._version for q in params), params[0].device, params[0].data_ptr())
+        key = (tuple(q._version for q in params), params[0].device,
+               0 if ops._is_fake(params[0]) else params[0].data_ptr())
         cached = self.__dict__.get("_mean_cache")
         if frozen and cached is not None and cached[0] == key:
             return cached[1], cached[2]
@@ -348,7 +349,7 @@ class SupervisedDetectorOutputsBase(nn.Module):
         frozen = not any(q.requires_grad for q in base)
         if frozen and ft_c is not None:
             # fine-tuning: the frozen [delta | bbox] block is packed once; only the small trainable block is re-packed
-            key = (tuple(q._version for q in base), base[0].device, base[0].data_ptr())
+            key = (tuple(q._version for q in base), base[0].device, 0 if ops._is_fake(base[0]) else base[0].data_ptr())
             cached = self.__dict__.get("_pack_cache")
             if cached is None or cached[0] != key:
                 cached = (key, torch.cat(base[:2], 0).detach(), torch.cat(base[2:], 0).detach())
@@ -385,7 +386,8 @@ class SupervisedDetectorOutputsBase(nn.Module):
         o_ft = K1 + K4
         o_vis = o_ft + (K1 + K4 if ft_c is not None else 0)
         rows = o_vis + K1
-        key = (tuple(q._version for q in frozen), tuple(q.data_ptr() for q in frozen), str(dev), rows)
+        fake = ops._is_fake(frozen[0])  # FakeTensor tracing: no data pointers, nothing to re-point
+        key = (tuple(q._version for q in frozen), () if fake else tuple(q.data_ptr() for q in frozen), str(dev), rows)
         pk = self.__dict__.get("_wpack")
         if pk is None or pk.key != key:
             old = pk
@@ -403,7 +405,7 @@ class SupervisedDetectorOutputsBase(nn.Module):
                 pk.b[o_vis:].copy_(ob)
             self.__dict__["_wpack"] = pk
             del old
-        if ft_c is not None:
+        if ft_c is not None and not fake:
             es = pk.W.element_size()
             want = ((ft_c.weight, pk.W[o_ft:o_ft + K1]), (ft_b.weight, pk.W[o_ft + K1:o_vis]),
                     (ft_c.bias, pk.b[o_ft:o_ft + K1]), (ft_b.bias, pk.b[o_ft + K1:o_vis]))
