@@ -134,6 +134,14 @@ int unit_fastrcnn_loss_packed(const float* scores, const float* deltas, const fl
                               const int64_t* gt_classes, int R, int K, float wx, float wy, float ww, float wh,
                               float smooth_l1_beta, float* losses, float* d_packed, int ld_packed, void* workspace,
                               size_t workspace_bytes, unit_stream_t stream);
+/* Unreduced (per-RoI) losses and their per-row gradients for FastRCNNOutputsReduction / NLL / Regression
+ * (modeling/roi_heads/fast_rcnn.py:24-130, weak_detector_fast_rcnn.py:23-37): row_ce [R] (nll != 0: scores are
+ * log-probabilities and row_ce = -scores[r][cls]); row_box [R,4] smooth-L1 per coordinate of the gt class's deltas
+ * (0 for background rows); d_scores [R,K+1] and d_box [R,4] their derivatives.  deltas may be NULL (class loss only). */
+int unit_fastrcnn_row_losses(const float* scores, const float* deltas, const float* proposals, const float* gt_boxes,
+                             const int64_t* gt_classes, int R, int K, float wx, float wy, float ww, float wh,
+                             float smooth_l1_beta, int nll, float* row_ce, float* row_box, float* d_scores, float* d_box,
+                             unit_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * fast_rcnn_inference for a batch of images in two launches.  Replaces [D2] fast_rcnn_inference(_single_image)

@@ -646,3 +646,52 @@ def test_fused_fastrcnn_loss_and_grads(ops):
         assert_close_rms(lb.detach().cpu(), loss_box.detach(), 1e-5, "loss_box")
         assert_close_rms(s2.grad.cpu(), scores.grad, 1e-5, "d scores")
         assert_close_rms(d2.grad.cpu(), deltas.grad, 1e-5, "d deltas")
+
+
+# ----------------------------------------------------------------------------------------------- torch.library layer
+def test_opcheck_custom_ops(ops):
+    """torch.library.opcheck on the registered ops: schema, fake implementation vs real outputs (shapes / dtypes /
+    devices), autograd registration and AOT dispatch -- for roi_align, iou_match, similarity_transfer, detect,
+    mask_paste and the predictor linear."""
+    from torch.library import opcheck
+
+    g = seeded(77)
+    dev = "cuda"
+    feat = torch.randn(2, 64, 25, 42, generator=g).to(dev).requires_grad_(True)
+    rois = _rois(2, 24, 400, 672, g).to(dev)
+    opcheck(torch.ops.unit_b200.roi_align, (feat, rois, 14, 14, 1 / 16, 0, True, True),
+            test_utils=("test_schema", "test_faketensor", "test_autograd_registration", "test_aot_dispatch_static"))
+    gout = torch.randn(48, 64, 14, 14, generator=g).to(dev)
+    opcheck(torch.ops.unit_b200.roi_align_backward, (gout, rois, 2, 64, 25, 42, 1 / 16, 0, True, True),
+            test_utils=("test_schema", "test_faketensor"))
+    gt = random_boxes(5, 400, 672, g, 32.0).to(dev)
+    pb = random_boxes(300, 400, 672, g, 16.0).to(dev)
+    go, po = ops.offsets_from_counts([5], torch.device(dev)), ops.offsets_from_counts([300], torch.device(dev))
+    opcheck(torch.ops.unit_b200.iou_match, (gt, go, pb, po, [0.5], [0, 1]), test_utils=("test_schema", "test_faketensor"))
+    # similarity + transfer (VOC: 15 base + 5 novel)
+    K, B, Nn, R = 20, 15, 5, 64
+    base, novel = list(range(15)), list(range(15, 20))
+    spec = ops.TransferSpec(K, base, novel, torch.device(dev),
+                            static={"cls": torch.softmax(torch.randn(Nn, B, generator=g), -1).to(dev),
+                                    "bbox": torch.softmax(torch.randn(Nn, B, generator=g), -1).to(dev)},
+                            wv={"cls": 0.5, "bbox": 0.5}, norm={"cls": 1, "bbox": 1}, vis_threshold=0.02)
+    vis = torch.randn(R, K + 1, generator=g).to(dev)
+    ds = torch.randn(R, K + 1, generator=g).to(dev)
+    pd = torch.randn(R, 4 * K, generator=g).to(dev)
+    opcheck(torch.ops.unit_b200.similarity_transfer,
+            (vis, spec.static["cls"], spec.static["bbox"], None, spec.base_i32, spec.novel_i32, spec.class_kind, ds, pd,
+             None, None, None, 0.02, [0.5, 0.5, 0.0], [1, 1, 0], True, False, 0, 3),
+            test_utils=("test_schema", "test_faketensor"))
+    probs = torch.softmax(torch.randn(300, K + 1, generator=g) * 2, -1).to(dev)
+    boxes = pb.repeat_interleave(K, 0).view(300, K * 4).contiguous()
+    hw = torch.tensor([[400.0, 672.0]], device=dev)
+    opcheck(torch.ops.unit_b200.detect, (boxes, probs, po, hw, 0.05, 0.5, 100, ops.NMS_TV_CUDA_RULE),
+            test_utils=("test_schema", "test_faketensor"))
+    masks = torch.rand(6, 28, 28, generator=g).to(dev)
+    opcheck(torch.ops.unit_b200.mask_paste, (masks, pb[:6].contiguous(), 400, 672, 0.5),
+            test_utils=("test_schema", "test_faketensor"))
+    x = torch.randn(256, 128, generator=g).to(dev)
+    w = (torch.randn(40, 128, generator=g) * 0.1).to(dev).requires_grad_(True)
+    b = torch.zeros(40, device=dev, requires_grad=True)
+    opcheck(torch.ops.unit_b200.predictor_linear, (x, w, b),
+            test_utils=("test_schema", "test_faketensor", "test_autograd_registration", "test_aot_dispatch_static"))

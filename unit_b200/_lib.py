@@ -68,6 +68,8 @@ _SIGNATURES = {
                                      POINTER(c_void_p), POINTER(c_void_p), c_int, P, c_size_t, P]),
     "unit_fastrcnn_loss_packed": (c_int, [P, P, P, P, P, c_int, c_int, c_float, c_float, c_float, c_float, c_float, P, P,
                                           c_int, P, c_size_t, P]),
+    "unit_fastrcnn_row_losses": (c_int, [P, P, P, P, P, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int,
+                                         P, P, P, P, P]),
     "unit_boxes_to_rois": (c_int, [P, P, c_int, c_int, P, P]),
     "unit_mil_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "unit_mil_loss": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P, c_size_t, P]),

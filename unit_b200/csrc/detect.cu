@@ -1144,6 +1144,66 @@ __global__ void fastrcnn_loss_kernel(const float* __restrict__ scores, const flo
   }
 }
 
+
+// Per-RoI (unreduced) Fast R-CNN losses and their per-row gradients -- FastRCNNOutputsReduction / NLL / Regression
+// (fast_rcnn.py:24-130, weak_detector_fast_rcnn.py:23-37).  One warp per RoI:
+//   row_ce[r]    = cross_entropy(scores[r], cls)            (nll != 0: -scores[r][cls], the input already is log-probs)
+//   row_box[r,j] = smooth_l1(deltas[r, 4 cls + j] - get_deltas(proposal, gt)[j])   for foreground rows, else 0
+//   d_scores[r]  = d row_ce[r] / d scores[r]      d_box[r,j] = d row_box[r,j] / d deltas[r, 4 cls + j]
+__global__ void row_losses_kernel(const float* __restrict__ scores, const float* __restrict__ deltas,
+                                  const float4* __restrict__ proposals, const float4* __restrict__ gt_boxes,
+                                  const int64_t* __restrict__ gt_classes, int R, int K, float wx, float wy, float ww,
+                                  float wh, float beta, int nll, float* __restrict__ row_ce, float* __restrict__ row_box,
+                                  float* __restrict__ d_scores, float* __restrict__ d_box) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int K1 = K + 1;
+  const int cls = (int)gt_classes[r];
+  const float* s = scores + (long long)r * K1;
+  if (nll) {
+    for (int k = lane; k < K1; k += 32) d_scores[(long long)r * K1 + k] = k == cls ? -1.f : 0.f;
+    if (lane == 0) row_ce[r] = -s[cls >= 0 && cls < K1 ? cls : 0];
+  } else {
+    float m = -INFINITY;
+    for (int k = lane; k < K1; k += 32) m = fmaxf(m, s[k]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int k = lane; k < K1; k += 32) sum += expf(s[k] - m);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float lse = m + logf(sum);
+    for (int k = lane; k < K1; k += 32) d_scores[(long long)r * K1 + k] = expf(s[k] - lse) - (k == cls ? 1.f : 0.f);
+    if (lane == 0) row_ce[r] = lse - s[cls >= 0 && cls < K1 ? cls : 0];
+  }
+  if (!deltas || lane >= 4) return;
+  float loss = 0.f, dv = 0.f;
+  if (cls >= 0 && cls < K) {
+    const float4 p = proposals[r], g = gt_boxes[r];
+    const float sw = __fsub_rn(p.z, p.x), sh = __fsub_rn(p.w, p.y);
+    const float scx = __fadd_rn(p.x, __fmul_rn(0.5f, sw)), scy = __fadd_rn(p.y, __fmul_rn(0.5f, sh));
+    const float tw = __fsub_rn(g.z, g.x), th = __fsub_rn(g.w, g.y);
+    const float tcx = __fadd_rn(g.x, __fmul_rn(0.5f, tw)), tcy = __fadd_rn(g.y, __fmul_rn(0.5f, th));
+    float t;
+    if (lane == 0) t = __fdiv_rn(__fmul_rn(wx, __fsub_rn(tcx, scx)), sw);
+    else if (lane == 1) t = __fdiv_rn(__fmul_rn(wy, __fsub_rn(tcy, scy)), sh);
+    else if (lane == 2) t = __fmul_rn(ww, logf(__fdiv_rn(tw, sw)));
+    else t = __fmul_rn(wh, logf(__fdiv_rn(th, sh)));
+    const float diff = deltas[(long long)r * 4 * K + 4 * cls + lane] - t;
+    const float n = fabsf(diff);
+    if (beta < 1e-5f) {
+      loss = n;
+      dv = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+    } else if (n < beta) {
+      loss = 0.5f * n * n / beta;
+      dv = diff / beta;
+    } else {
+      loss = n - 0.5f * beta;
+      dv = diff > 0.f ? 1.f : -1.f;
+    }
+  }
+  row_box[(long long)r * 4 + lane] = loss;
+  d_box[(long long)r * 4 + lane] = dv;
+}
+
 __global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int R, float* __restrict__ out) {
   __shared__ float s0[32], s1[32];
   float a = 0.f, b = 0.f;
@@ -1226,5 +1286,22 @@ extern "C" int unit_fastrcnn_loss(const float* scores, const float* deltas, cons
   UNIT_CHECK_LAUNCH("fastrcnn_loss_kernel");
   unit::detect::loss_reduce_kernel<<<1, 1024, 0, st>>>((const float*)workspace, R, losses);
   UNIT_CHECK_LAUNCH("loss_reduce_kernel");
+  return UNIT_OK;
+}
+
+extern "C" int unit_fastrcnn_row_losses(const float* scores, const float* deltas, const float* proposals,
+                                        const float* gt_boxes, const int64_t* gt_classes, int R, int K, float wx,
+                                        float wy, float ww, float wh, float smooth_l1_beta, int nll, float* row_ce,
+                                        float* row_box, float* d_scores, float* d_box, unit_stream_t stream) {
+  UNIT_REQUIRE(R >= 0 && K > 0, "fastrcnn_row_losses: bad shape");
+  if (R == 0) return UNIT_OK;
+  UNIT_REQUIRE(scores && gt_classes && row_ce && d_scores, "fastrcnn_row_losses: null pointer");
+  UNIT_REQUIRE(!deltas || (proposals && gt_boxes && row_box && d_box), "fastrcnn_row_losses: box inputs missing");
+  UNIT_REQUIRE((((uintptr_t)proposals | (uintptr_t)gt_boxes) & 15) == 0,
+               "fastrcnn_row_losses: boxes must be 16-byte aligned");
+  unit::detect::row_losses_kernel<<<cdiv((long long)R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      scores, deltas, (const float4*)proposals, (const float4*)gt_boxes, gt_classes, R, K, wx, wy, ww, wh,
+      smooth_l1_beta, nll, row_ce, row_box, d_scores, d_box);
+  UNIT_CHECK_LAUNCH("row_losses_kernel");
   return UNIT_OK;
 }

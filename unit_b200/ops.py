@@ -377,6 +377,53 @@ def fastrcnn_loss(scores, deltas, proposals, gt_boxes, gt_classes, weights=(10.0
     return _FastRCNNLossFn.apply(scores, deltas, proposals, gt_boxes, gt_classes, tuple(weights), float(beta))
 
 
+class _RowLossesFn(torch.autograd.Function):
+    """Per-RoI Fast R-CNN losses (FastRCNNOutputsReduction / NLL / Regression) with their gradients from one launch."""
+
+    @staticmethod
+    def forward(ctx, scores, deltas, proposals, gt_boxes, gt_classes, weights, beta, nll):
+        dev = _need_cuda(scores)
+        scores = _c(scores, _F32)
+        R, K1 = scores.shape
+        K = K1 - 1
+        gt_classes = _c(gt_classes, torch.int64)
+        row_ce = torch.empty((R,), dtype=_F32, device=dev)
+        d_scores = torch.empty_like(scores)
+        has_box = deltas is not None
+        row_box = torch.zeros((R, 4), dtype=_F32, device=dev)
+        d_box = torch.zeros((R, 4), dtype=_F32, device=dev)
+        if has_box:
+            deltas = _c(deltas, _F32)
+        check(lib().unit_fastrcnn_row_losses(_ptr(scores), _ptr(deltas) if has_box else None,
+                                             _ptr(_c(proposals, _F32)) if has_box else None,
+                                             _ptr(_c(gt_boxes, _F32)) if has_box else None, _ptr(gt_classes), R, K,
+                                             float(weights[0]), float(weights[1]), float(weights[2]), float(weights[3]),
+                                             float(beta), int(bool(nll)), _ptr(row_ce), _ptr(row_box), _ptr(d_scores),
+                                             _ptr(d_box), _stream()), "unit_fastrcnn_row_losses")
+        ctx.save_for_backward(d_scores, d_box, gt_classes)
+        ctx.K, ctx.has_box = K, has_box
+        return row_ce, row_box
+
+    @staticmethod
+    def backward(ctx, g_ce, g_box):
+        d_scores, d_box, gt_classes = ctx.saved_tensors
+        g_scores = d_scores * g_ce[:, None]
+        g_deltas = None
+        if ctx.has_box and ctx.needs_input_grad[1]:
+            K = ctx.K
+            g_deltas = torch.zeros((d_scores.shape[0], 4 * K), dtype=_F32, device=d_scores.device)
+            fg = ((gt_classes >= 0) & (gt_classes < K)).nonzero().squeeze(1)
+            cols = 4 * gt_classes[fg][:, None] + torch.arange(4, device=fg.device)
+            g_deltas[fg[:, None], cols] = (d_box * g_box)[fg]
+        return g_scores, g_deltas, None, None, None, None, None, None
+
+
+def fastrcnn_row_losses(scores, deltas, proposals, gt_boxes, gt_classes, weights=(10.0, 10.0, 5.0, 5.0), beta=0.0,
+                        nll=False):
+    """-> (row_ce [R], row_box [R,4]) differentiable w.r.t. scores / deltas."""
+    return _RowLossesFn.apply(scores, deltas, proposals, gt_boxes, gt_classes, tuple(weights), float(beta), bool(nll))
+
+
 # ---------------------------------------------------------------------------------- weak-image training losses
 class _MILLossFn(torch.autograd.Function):
     """weak_detector_fast_rcnn.py:189-214 fused with its gradient: (loss_im_cls, mil_scores, class_vector)."""

@@ -191,9 +191,8 @@ def similarity_transfer(vis_logits: Optional[Tensor], static_cls: Optional[Tenso
     heads = tuple(h for i, h in enumerate(("cls", "bbox", "seg")) if (want >> i) & 1)
     s, b, sims = _k._similarity_transfer_forward_impl(spec, vis_logits, delta_scores, proposal_deltas, weak_scores,
                                                       ft_scores, ft_deltas, do_transfer, novel_neg_inf, heads)
-    e = s.new_empty((0,))
-    return s, b, sims["cls"] if sims["cls"] is not None else e, sims["bbox"] if sims["bbox"] is not None else e, \
-        sims["seg"] if sims["seg"] is not None else e
+    pick = lambda t: t if t is not None else s.new_empty((0,))  # a fresh tensor each: outputs must not alias
+    return s, b, pick(sims["cls"]), pick(sims["bbox"]), pick(sims["seg"])
 
 
 @similarity_transfer.register_fake
