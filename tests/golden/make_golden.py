@@ -10,6 +10,8 @@ The fixtures pin oracle.unit_ref (and through it the CUDA path) to what the auth
   weak_label.pt     weak_detector_fast_rcnn.py label_and_sample_proposals (pairwise_iou + UniT Matcher)
   weak_losses.pt    weak_detector_fast_rcnn.py WeakDetectorOutputsBase.forward + losses (MIL + 3 OICR refinements),
                     the per-iteration compute_loss_inputs outputs and the gradients of the summed loss
+  outputs_variants.pt  fast_rcnn.py FastRCNNOutputsReduction / NLL / Regression (+ the weak detector's Regression) losses
+                    and gradients, [D2] predict_boxes_for_gt_classes
   glove_mean.pt     the reference's only shipped data fixture, re-saved as a bare tensor
 """
 from __future__ import annotations
@@ -278,6 +280,61 @@ def make_weak_losses(ns):
             "grad_x": grads[5]}
 
 
+def make_outputs_variants(ns):
+    """fast_rcnn.py:24-130 FastRCNNOutputsReduction / NLL / Regression and weak_detector_fast_rcnn.py:23-37, run
+    verbatim on seeded predictions (losses + gradients), plus [D2] predict_boxes_for_gt_classes (restated D2 glue)."""
+    import types as _types
+
+    from oracle.d2.modeling import FastRCNNOutputLayers
+    from oracle.d2.ops import Box2BoxTransform
+
+    g = _seeded(71)
+    K, img = 20, (600, 800)
+    counts = (70, 58)
+    b2b = Box2BoxTransform(weights=(10.0, 10.0, 5.0, 5.0))
+    props = []
+    for n in counts:
+        pb = boxes_in_image(n, img[0], img[1], g, 16.0)
+        gt = pb + torch.randn(n, 4, generator=g) * 6
+        gt[:, 2:] = torch.maximum(gt[:, 2:], gt[:, :2] + 4)
+        cls = torch.randint(0, K + 1, (n,), generator=g)
+        props.append(Instances(img, proposal_boxes=Boxes(pb), gt_boxes=Boxes(gt), gt_classes=cls))
+    R = sum(counts)
+    scores = (2.0 * torch.randn(R, K + 1, generator=g)).requires_grad_(True)
+    deltas = (0.5 * torch.randn(R, 4 * K, generator=g)).requires_grad_(True)
+    weights = torch.rand(R, generator=g)
+    out = {"image_size": img, "proposal_boxes": [p.proposal_boxes.tensor for p in props],
+           "gt_boxes": [p.gt_boxes.tensor for p in props], "gt_classes": [p.gt_classes for p in props],
+           "scores": scores.detach().clone(), "deltas": deltas.detach().clone(), "weights": weights, "cases": {}}
+
+    def run(tag, obj, reduce):
+        losses = obj.losses()
+        total = sum(reduce(v) for v in losses.values())
+        gs, gd = torch.autograd.grad(total, [scores, deltas], allow_unused=True)
+        out["cases"][tag] = {"losses": {k: v.detach().clone() for k, v in losses.items()}, "grad_scores": gs,
+                             "grad_deltas": gd}
+
+    F = ns.fast_rcnn
+    for beta in (0.0, 0.4):
+        run(f"reduction_beta{beta}", F.FastRCNNOutputsReduction(b2b, scores, deltas, props, beta, "smooth_l1"),
+            lambda v: (v * torch.linspace(0.5, 1.5, v.numel()).view(v.shape)).sum())
+        run(f"regression_beta{beta}", F.FastRCNNOutputsRegression(b2b, scores, deltas, props, weights, beta, "smooth_l1"),
+            lambda v: v)
+        run(f"weak_regression_beta{beta}",
+            ns.weak.FastRCNNOutputsRegression(b2b, scores, deltas, props, weights, beta, "smooth_l1"), lambda v: v)
+    logp = torch.log_softmax(scores, -1)
+    nll = F.FastRCNNOutputsNLL(b2b, logp, deltas, props, 0.0, "smooth_l1")
+    losses = nll.losses()
+    gs, gd = torch.autograd.grad(sum(losses.values()), [scores, deltas])
+    out["cases"]["nll"] = {"losses": {k: v.detach().clone() for k, v in losses.items()}, "grad_scores": gs,
+                           "grad_deltas": gd}
+    holder = _types.SimpleNamespace(box2box_transform=b2b)
+    with torch.no_grad():
+        pb = FastRCNNOutputLayers.predict_boxes_for_gt_classes(holder, (scores.detach(), deltas.detach()), props)
+    out["pred_boxes_for_gt_classes"] = [b.clone() for b in pb]
+    return out
+
+
 def main():
     assert shim.reference_available(), "needs /root/reference"
     ns = shim.load_reference()
@@ -304,6 +361,7 @@ def main():
         "mask_head.pt": make_mask_head(ns),
         "weak_label.pt": make_weak_label(ns),
         "weak_losses.pt": make_weak_losses(ns),
+        "outputs_variants.pt": make_outputs_variants(ns),
     }
     only = set(sys.argv[1:])  # optional: regenerate just the named fixtures
     for name, obj in fixtures.items():

@@ -495,3 +495,48 @@ def test_finetune_similarity_gradient_reaches_box_features(registry):
     # frozen features (the shipped VOC split-1 setting): no graph is built through the similarity
     sim2 = head.get_similarity_matrices(x0.cuda())
     assert not sim2.vis_logits.requires_grad
+
+
+def test_outputs_variants_match_reference_fixture():
+    """FastRCNNOutputsReduction / NLL / Regression (fast_rcnn.py:24-130, weak_detector_fast_rcnn.py:23-37) and
+    predict_boxes_for_gt_classes vs the reference run verbatim (tests/golden/outputs_variants.pt): losses and the
+    gradients w.r.t. scores / deltas."""
+    from unit_b200 import outputs
+    from unit_b200.layers import Box2BoxTransform
+    from unit_b200.structures import Boxes, Instances
+
+    gold = load_golden("outputs_variants.pt")
+    img = tuple(gold["image_size"])
+    props = [Instances(img, proposal_boxes=Boxes(pb.cuda()), gt_boxes=Boxes(gb.cuda()), gt_classes=gc.cuda())
+             for pb, gb, gc in zip(gold["proposal_boxes"], gold["gt_boxes"], gold["gt_classes"])]
+    b2b = Box2BoxTransform(weights=(10.0, 10.0, 5.0, 5.0))
+    weights = gold["weights"].cuda()
+
+    def check(tag, make, reduce, transform=None):
+        scores = gold["scores"].clone().cuda().requires_grad_(True)
+        deltas = gold["deltas"].clone().cuda().requires_grad_(True)
+        obj = make(transform(scores) if transform else scores, deltas)
+        losses = obj.losses()
+        ref = gold["cases"][tag]
+        assert set(losses) == set(ref["losses"]), (tag, set(losses))
+        for k, v in losses.items():
+            assert v.shape == ref["losses"][k].shape, (tag, k, v.shape, ref["losses"][k].shape)
+            assert_close_rms(v.detach().cpu(), ref["losses"][k], 2e-5, f"{tag}.{k}")
+        total = sum(reduce(v) for v in losses.values())
+        total.backward()
+        assert_close_rms(scores.grad.cpu(), ref["grad_scores"], 2e-5, f"{tag} d/dscores")
+        assert_close_rms(deltas.grad.cpu(), ref["grad_deltas"], 2e-5, f"{tag} d/ddeltas")
+
+    lin = lambda v: (v * torch.linspace(0.5, 1.5, v.numel()).view(v.shape).to(v.device)).sum()
+    for beta in (0.0, 0.4):
+        check(f"reduction_beta{beta}", lambda s, d: outputs.FastRCNNOutputsReduction(b2b, s, d, props, beta), lin)
+        check(f"regression_beta{beta}", lambda s, d: outputs.FastRCNNOutputsRegression(b2b, s, d, props, weights, beta),
+              lambda v: v)
+        check(f"weak_regression_beta{beta}",
+              lambda s, d: outputs.FastRCNNOutputsRegression(b2b, s, d, props, weights, beta), lambda v: v)
+    check("nll", lambda s, d: outputs.FastRCNNOutputsNLL(b2b, s, d, props, 0.0), lambda v: v,
+          transform=lambda s: torch.log_softmax(s, -1))
+    with torch.no_grad():
+        pb = outputs.predict_boxes_for_gt_classes(b2b, (gold["scores"].cuda(), gold["deltas"].cuda()), props)
+    for a, b in zip(pb, gold["pred_boxes_for_gt_classes"]):
+        assert_close_rms(a.cpu(), b, 1e-5, "predict_boxes_for_gt_classes")

@@ -377,11 +377,27 @@ __global__ void mask_transfer_kernel(const float* __restrict__ logits, const flo
                                      const float* __restrict__ x_delta, const int64_t* __restrict__ pred_classes,
                                      float* __restrict__ out_logits, float* __restrict__ out_probs, int K, int B,
                                      int Nn, int MM) {
+  // grid = (detections, chunks): the chunks of one detection split its pixels (and, for the full-logits output, its
+  // (class, pixel) pairs), so that 100 detections fill the GPU instead of 100 SMs running 60-long dependent chains
   const int d = blockIdx.x;
+  const int nchunk = gridDim.y, chunk = blockIdx.y;
   const float* lg = logits + (long long)d * K * MM;
   const float* S = s_seg ? s_seg + (s_is_2d ? 0 : (long long)d * Nn * B) : nullptr;
+  // base-class combination of one pixel: four independent accumulators (the loads of a round are all in flight)
+  auto combine = [&](const float* sr, int m) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = 0;
+    for (; b + 4 <= B; b += 4) {
+      a0 = fmaf(sr[b], lg[base[b] * MM + m], a0);
+      a1 = fmaf(sr[b + 1], lg[base[b + 1] * MM + m], a1);
+      a2 = fmaf(sr[b + 2], lg[base[b + 2] * MM + m], a2);
+      a3 = fmaf(sr[b + 3], lg[base[b + 3] * MM + m], a3);
+    }
+    for (; b < B; ++b) a0 = fmaf(sr[b], lg[base[b] * MM + m], a0);
+    return (a0 + a1) + (a2 + a3);
+  };
   if (out_logits) {
-    for (int i = threadIdx.x; i < K * MM; i += blockDim.x) {
+    for (int i = chunk * blockDim.x + threadIdx.x; i < K * MM; i += nchunk * blockDim.x) {
       const int k = i / MM, m = i - k * MM;
       float v = lg[i];
       if (S) {
@@ -389,7 +405,7 @@ __global__ void mask_transfer_kernel(const float* __restrict__ logits, const flo
         if (kind >= NOVEL_TAG) {
           const float* sr = S + (kind - NOVEL_TAG) * B;
           float acc = 0.f;
-          for (int b = 0; b < B; ++b) acc = fmaf(sr[b], lg[base[b] * MM + m], acc);
+          for (int b = 0; b < B; ++b) acc = fmaf(sr[b], lg[base[b] * MM + m], acc);  // reference summation order
           v = acc;
         } else if (kind < 0) {
           v = 0.f;
@@ -402,14 +418,11 @@ __global__ void mask_transfer_kernel(const float* __restrict__ logits, const flo
   if (out_probs) {
     const int k = (int)pred_classes[d];
     const int kind = class_kind[k];
-    for (int m = threadIdx.x; m < MM; m += blockDim.x) {
+    for (int m = chunk * blockDim.x + threadIdx.x; m < MM; m += nchunk * blockDim.x) {
       float v = lg[k * MM + m];
       if (S) {
         if (kind >= NOVEL_TAG) {
-          const float* sr = S + (kind - NOVEL_TAG) * B;
-          float acc = 0.f;
-          for (int b = 0; b < B; ++b) acc = fmaf(sr[b], lg[base[b] * MM + m], acc);
-          v = acc;
+          v = combine(S + (kind - NOVEL_TAG) * B, m);
         } else if (kind < 0) {
           v = 0.f;
         }
@@ -575,6 +588,54 @@ __global__ void __launch_bounds__(256) mask_paste_window_kernel(const float* __r
   }
 }
 
+// Same windows, four pixels per thread: the canvas of one detection is H * W bytes with H * W % 4 == 0, so it is a
+// whole number of aligned 32-bit words; a thread evaluates the 4 pixels of one word (a word may begin up to 3 pixels
+// before the window's first column, or run into the next image row -- every pixel is evaluated at its own (y, x), so a
+// word shared by two rows of the window is written twice with identical contents) and issues ONE 4-byte store: a warp
+// writes 128 contiguous bytes instead of 32.
+__global__ void __launch_bounds__(256) mask_paste_window4_kernel(const float* __restrict__ masks,
+                                                                 const float4* __restrict__ boxes, int M, int H, int W,
+                                                                 float thr, uint8_t* __restrict__ out) {
+  const int d = blockIdx.y;
+  const float4 bx = __ldg(boxes + d);
+  const float bw = bx.z - bx.x, bh = bx.w - bx.y;
+  int x_lo = 0, x_hi = W - 1, y_lo = 0, y_hi = H - 1;
+  if (bw > 0.f && bh > 0.f && bw < 1e6f && bh < 1e6f && fabsf(bx.x) < 1e6f && fabsf(bx.y) < 1e6f) {
+    const float mx = bw / (float)M + 1.f, my = bh / (float)M + 1.f;
+    x_lo = max(0, (int)floorf(bx.x - mx - 0.5f));
+    x_hi = min(W - 1, (int)ceilf(bx.z + mx - 0.5f));
+    y_lo = max(0, (int)floorf(bx.y - my - 0.5f));
+    y_hi = min(H - 1, (int)ceilf(bx.w + my - 0.5f));
+  }
+  const int r0 = max(y_lo, (int)blockIdx.x * WIN_ROWS), r1 = min(y_hi, (int)blockIdx.x * WIN_ROWS + WIN_ROWS - 1);
+  if (r0 > r1 || x_lo > x_hi) return;
+  const float* mk = masks + (long long)d * M * M;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(out + (long long)d * H * W);
+  const int nw = ((x_hi - x_lo) >> 2) + 2;  // words per row, upper bound
+  const int n = (r1 - r0 + 1) * nw;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int y = r0 + i / nw, k = i - (i / nw) * nw;
+    const int first = (y * W + x_lo) >> 2, last = (y * W + x_hi) >> 2;
+    const int w = first + k;
+    if (w > last) continue;
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int x = 4 * w + j - y * W, yy = y;
+      if (x < 0) {
+        x += W;
+        --yy;
+      } else if (x >= W) {
+        x -= W;
+        ++yy;
+      }
+      if (yy >= y_lo && yy <= y_hi && x >= x_lo && x <= x_hi)
+        word |= (uint32_t)paste_pixel(mk, M, bx, x, yy, thr) << (8 * j);
+    }
+    dst[w] = word;
+  }
+}
+
 }  // namespace transfer
 }  // namespace unit
 
@@ -692,8 +753,12 @@ int unit_mask_transfer(const float* logits, const float* s_seg, int s_is_2d, con
   UNIT_REQUIRE(logits && class_kind && (out_logits || out_probs), "mask_transfer: null pointer");
   UNIT_REQUIRE(!out_probs || pred_classes, "mask_transfer: out_probs needs pred_classes");
   UNIT_REQUIRE(!s_seg || base, "mask_transfer: similarity given without base indices");
-  mask_transfer_kernel<<<D, 256, 0, (cudaStream_t)stream>>>(logits, s_seg, s_is_2d, base, class_kind, x_delta,
-                                                            pred_classes, out_logits, out_probs, K, B, Nn, MM);
+  // probabilities only (inference): one thread per pixel; full logits: a few chunks of (class, pixel) pairs
+  const int threads = 128;
+  const int chunks = out_logits ? 8 : (MM + threads - 1) / threads;
+  dim3 grid(D, chunks);
+  mask_transfer_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(logits, s_seg, s_is_2d, base, class_kind, x_delta,
+                                                                  pred_classes, out_logits, out_probs, K, B, Nn, MM);
   UNIT_CHECK_LAUNCH("mask_transfer_kernel");
   return UNIT_OK;
 }
@@ -708,8 +773,12 @@ int unit_mask_paste(const float* masks, const float* boxes, int D, int M, int im
   if (threshold > 0.f && D <= 65535 && !switches().paste_flat) {  // outside value is 0: clear, then visit the box windows only
     UNIT_CUDA(cudaMemsetAsync(out, 0, (size_t)total, (cudaStream_t)stream));
     dim3 grid(cdiv(img_h, unit::transfer::WIN_ROWS), D);
-    mask_paste_window_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(masks, (const float4*)boxes, M, img_h, img_w,
-                                                                     threshold, out);
+    if (((long long)img_h * img_w) % 4 == 0 && (((uintptr_t)out) & 3) == 0 && img_w >= 8)
+      mask_paste_window4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(masks, (const float4*)boxes, M, img_h, img_w,
+                                                                        threshold, out);
+    else
+      mask_paste_window_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(masks, (const float4*)boxes, M, img_h, img_w,
+                                                                       threshold, out);
     UNIT_CHECK_LAUNCH("mask_paste_window_kernel");
     return UNIT_OK;
   }

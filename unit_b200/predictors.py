@@ -514,6 +514,12 @@ class SupervisedDetectorOutputsBase(nn.Module):
         boxes = layers.cat([p.proposal_boxes.tensor for p in proposals])
         return self.box2box_transform.apply_deltas(proposal_deltas, boxes).split([len(p) for p in proposals])
 
+    def predict_boxes_for_gt_classes(self, predictions, proposals):
+        """[D2] FastRCNNOutputLayers.predict_boxes_for_gt_classes (roi_heads.py:535-539, TRAIN_ON_PRED_BOXES)."""
+        from .outputs import predict_boxes_for_gt_classes
+
+        return predict_boxes_for_gt_classes(self.box2box_transform, predictions, proposals)
+
     def inference(self, predictions, proposals, tta=False):
         """fast_rcnn.py:455-468: softmax + decode in one launch, then batched filter + NMS."""
         scores, proposal_deltas = predictions

@@ -443,8 +443,11 @@ class WSROIHeadNoMeta(WSROIHead):
             losses = self.box_predictor.losses(predictions, proposals, weak_predictions=weak_predictions,
                                                weak_proposals=weak_proposals, weak_targets=weak_targets,
                                                train_only_weak=train_only_weak)
-            if self.train_on_pred_boxes:
-                raise NotImplementedError("TRAIN_ON_PRED_BOXES is False in every reference YAML")
+            if self.train_on_pred_boxes:  # roi_heads.py:533-539: the next stage trains on the predicted boxes
+                with torch.no_grad():
+                    pred_boxes = self.box_predictor.predict_boxes_for_gt_classes(predictions, proposals)
+                    for per_image, boxes_i in zip(proposals, pred_boxes):
+                        per_image.proposal_boxes = Boxes(boxes_i)
             return losses, box_features, similarity
         pred_instances, filter_inds = self.box_predictor.inference(predictions, proposals, tta=tta)
         if return_similarity and not tta:
