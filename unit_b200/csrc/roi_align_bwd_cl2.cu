@@ -227,7 +227,8 @@ __device__ __noinline__ void direct_row(const Params& p, const RoiTab* t, const 
 // One x-sample of the horizontal sweep as ONE block of PTX, so that the window keeps its registers on both paths and
 // the (warp-uniform) branch needs no reconvergence bookkeeping:   c0 += hx * v;  c1 += lx * v;
 // last sample of its column (F_ADV): reduce c0 into *cell, cell += cstep, c0 = c1, c1 = 0.
-__device__ __forceinline__ void sweep_step(f2& c0, f2& c1, char*& cell, float2 e, f2 v, long long cstep) {
+__device__ __forceinline__ void sweep_step(f2& c0, f2& c1, char*& cell, float2 e, f2 v, long long cstep,
+                                           uint64_t red_policy) {
   asm volatile(
       "{\n"
       ".reg .pred q;\n"
@@ -244,7 +245,11 @@ __device__ __forceinline__ void sweep_step(f2& c0, f2& c1, char*& cell, float2 e
       "@q bra.uni SWEEP_NEXT;\n"
 #ifndef UNIT_BWD_NORED
       "mov.b64 {ra, rb}, %0;\n"
+#ifdef UNIT_BWD2_RED_HINT
+      "red.global.add.L2::cache_hint.v2.f32 [%2], {ra, rb}, %7;\n"
+#else
       "red.global.add.v2.f32 [%2], {ra, rb};\n"
+#endif
 #endif
       "add.s64 %2, %2, %6;\n"
       "mov.b64 %0, %1;\n"
@@ -252,14 +257,14 @@ __device__ __forceinline__ void sweep_step(f2& c0, f2& c1, char*& cell, float2 e
       "SWEEP_NEXT:\n"
       "}\n"
       : "+l"(c0), "+l"(c1), "+l"(cell)
-      : "f"(e.x), "f"(e.y), "l"(v), "l"(cstep)
+      : "f"(e.x), "f"(e.y), "l"(v), "l"(cstep), "l"(red_policy)
       : "memory");
 }
 
 // Horizontal sweep of one finished feature row: v[pw] (two channels per lane) is spread over the row's cells with a
 // two-column window (c0, c1); c0 is complete when the lower tap column advances -> one red.v2 per (cell, lane).
 __device__ __forceinline__ void sweep(const float2* __restrict__ xt, const f2 (&v)[P], char* cell, long long cstep,
-                                      int gw) {
+                                      int gw, uint64_t red_policy) {
   f2 c0 = 0ull, c1 = 0ull;
   float2 en = *xt;
 #pragma unroll
@@ -268,7 +273,7 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ xt, const f2 (&
     for (int ix = 0; ix < gw; ++ix) {
       const float2 e = en;
       en = *++xt;  // one entry ahead (the table has spare entries past the last sample)
-      sweep_step(c0, c1, cell, e, v[pw], cstep);
+      sweep_step(c0, c1, cell, e, v[pw], cstep, red_policy);
     }
   }
 #ifndef UNIT_BWD_NORED
@@ -285,6 +290,8 @@ __global__ void __launch_bounds__(NT, 1) roi_align_bwd_cl2(const __grid_constant
   uint64_t policy;
   if (p.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
   else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(policy));
+  uint64_t red_policy;  // experiment (-DUNIT_BWD2_RED_HINT): keep the 34 MB gradient image resident against the stream
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(red_policy));
   if (lane == 0) {
     for (int b = 0; b < NST; ++b) mbar_init(&wa->bar[b], 1);
     mbar_init(&wa->tbar[0], 1);
@@ -372,7 +379,7 @@ __global__ void __launch_bounds__(NT, 1) roi_align_bwd_cl2(const __grid_constant
 #pragma unroll
           for (int pw = 0; pw < P; ++pw) fma2(vlo[pw], hy, g2[pw]);
           if (__float_as_uint(e.x) & F_ADV) {  // last sample whose lower tap is this feature row: sweep it
-            sweep(xt, vlo, rowp, cstep, gw);
+            sweep(xt, vlo, rowp, cstep, gw, red_policy);
             rowp += rstep;
 #pragma unroll
             for (int pw = 0; pw < P; ++pw) {
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(NT, 1) roi_align_bwd_cl2(const __grid_constant
           }
         }
       }
-      sweep(xt, vlo, rowp, cstep, gw);  // the row that only received upper taps
+      sweep(xt, vlo, rowp, cstep, gw, red_policy);  // the row that only received upper taps
     } else {
       // degenerate / foreign RoIs (mode 0) only drain their tiles; mode 2 evaluates every tap directly
 #pragma unroll 1
