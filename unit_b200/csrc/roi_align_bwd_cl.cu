@@ -525,6 +525,7 @@ roi_align_bwd_cl(const __grid_constant__ CUtensorMap gmap, const Params p) {
         if (lane == 0) refill(cur, nxt, k, b);
       }
     }
+    __syncwarp();  // every lane has finished reading this item's tables before the next item rebuilds them
     cur = nxt;
     nxt = cur < n_items ? fetch() : n_items;
   }

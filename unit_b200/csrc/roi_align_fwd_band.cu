@@ -296,15 +296,19 @@ __device__ __forceinline__ void store4(T* __restrict__ dst, f2 a, f2 b, bool wri
 }
 
 template <typename T, int NB, int GH>
-__device__ __forceinline__ void task_band(const float4* __restrict__ rowp, int W, int gh, int nb,
+__device__ __forceinline__ void task_band(const float4* __restrict__ rowp, int W, int nrows, int gh, int nb,
                                           const float (&w)[MAXB], const float2* __restrict__ yt,
                                           T* __restrict__ dst, bool writer) {
   constexpr int NV = NB > 0 ? NB : MAXB;
   float4 v[NV];
+  int rows_left = nrows;  // footprint rows not yet requested (warp-uniform): the look-ahead never leaves the slab
   auto load_row = [&]() {
+    if (rows_left > 0) {
 #pragma unroll
-    for (int j = 0; j < NV; ++j)
-      if (NB > 0 || j < nb) v[j] = rowp[j];
+      for (int j = 0; j < NV; ++j)
+        if (NB > 0 || j < nb) v[j] = rowp[j];
+    }
+    --rows_left;
     rowp += W;
   };
   auto row_sum = [&](f2& hA, f2& hB) {
@@ -324,7 +328,7 @@ __device__ __forceinline__ void task_band(const float4* __restrict__ rowp, int W
   row_sum(hcA, hcB);
   load_row();
   row_sum(hnA, hnB);
-  load_row();  // one row ahead; a read past the footprint stays inside the slab / work areas and is never used
+  load_row();  // one row ahead (skipped past the footprint's last row)
   const int ng = GH > 0 ? GH : gh;
   float2 en = *yt;  // the table entry is requested one sample ahead (the table has spare entries past the last one)
 #pragma unroll 1
@@ -454,7 +458,7 @@ __global__ void __launch_bounds__(NT, 1) roi_align_fwd_band(const Params p, cons
       parity ^= 1u;
       // ---- consume the x-part into registers; the y-part stays in its buffer for the walk
       const RoiTabX* t = &wa->tx;
-      const int mode = t->mode, gw = t->gw, gh = t->gh, nb = t->nb, y0 = t->y0;
+      const int mode = t->mode, gw = t->gw, gh = t->gh, nb = t->nb, y0 = t->y0, nrows = t->nrows;
       // which (output column, channel quad) this lane owns for this RoI; 4 lanes shadow an owner and never store
       const int lm = t->lmap[lane];
       const bool writer = (lm & 0x80) == 0;
@@ -491,9 +495,9 @@ __global__ void __launch_bounds__(NT, 1) roi_align_fwd_band(const Params p, cons
           const float4* rowp = quad + (size_t)y0 * p.W + bx;
 #define UNIT_BAND_CASE(NBV)                                                                            \
   {                                                                                                    \
-    if (gh == 1) task_band<T, NBV, 1>(rowp, p.W, gh, nb, w, yt, stage_lane, writer);                   \
-    else if (gh == 2) task_band<T, NBV, 2>(rowp, p.W, gh, nb, w, yt, stage_lane, writer);              \
-    else task_band<T, NBV, 0>(rowp, p.W, gh, nb, w, yt, stage_lane, writer);                           \
+    if (gh == 1) task_band<T, NBV, 1>(rowp, p.W, nrows, gh, nb, w, yt, stage_lane, writer);            \
+    else if (gh == 2) task_band<T, NBV, 2>(rowp, p.W, nrows, gh, nb, w, yt, stage_lane, writer);       \
+    else task_band<T, NBV, 0>(rowp, p.W, nrows, gh, nb, w, yt, stage_lane, writer);                    \
   }
           if (nb <= 2) UNIT_BAND_CASE(2)
           else if (nb == 3) UNIT_BAND_CASE(3)
