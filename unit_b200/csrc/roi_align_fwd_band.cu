@@ -301,15 +301,15 @@ __device__ __forceinline__ void task_band(const float4* __restrict__ rowp, int W
                                           T* __restrict__ dst, bool writer) {
   constexpr int NV = NB > 0 ? NB : MAXB;
   float4 v[NV];
-  int rows_left = nrows;  // footprint rows not yet requested (warp-uniform): the look-ahead never leaves the slab
+  // The walk requests one row ahead; past the footprint's last row the pointer stops advancing, so the look-ahead
+  // re-reads that row (never used) instead of running into the other warps' work areas.
+  int rows_left = nrows;  // warp-uniform
   auto load_row = [&]() {
-    if (rows_left > 0) {
 #pragma unroll
-      for (int j = 0; j < NV; ++j)
-        if (NB > 0 || j < nb) v[j] = rowp[j];
-    }
+    for (int j = 0; j < NV; ++j)
+      if (NB > 0 || j < nb) v[j] = rowp[j];
     --rows_left;
-    rowp += W;
+    rowp += rows_left > 0 ? W : 0;
   };
   auto row_sum = [&](f2& hA, f2& hB) {
     hA = hB = 0ull;
@@ -328,7 +328,7 @@ __device__ __forceinline__ void task_band(const float4* __restrict__ rowp, int W
   row_sum(hcA, hcB);
   load_row();
   row_sum(hnA, hnB);
-  load_row();  // one row ahead (skipped past the footprint's last row)
+  load_row();  // one row ahead
   const int ng = GH > 0 ? GH : gh;
   float2 en = *yt;  // the table entry is requested one sample ahead (the table has spare entries past the last one)
 #pragma unroll 1
