@@ -618,7 +618,7 @@ def run_ours(args):
         achieved = alg_bytes / (kernel_ms[dom] * 1e-3) / 1e9
         traffic = None
         try:  # measured DRAM bytes per launch of that kernel (ncu --set full, see profiles/)
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
                 traffic = int(json.load(f)[dom]["dram_bytes"]) if dtype == torch.float32 else None
         except Exception:
             traffic = None

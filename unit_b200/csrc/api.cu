@@ -51,6 +51,7 @@ const Switches& switches() {
     v.roi_debug = env_int("UNIT_ROI_DEBUG", 0);
     v.bwd_promo = env_int("UNIT_ROI_BWD_PROMO", 2);
     v.bwd_evict_first = env_int("UNIT_ROI_BWD_EVICT_FIRST", 1);
+    v.bwd2_evict_first = env_int("UNIT_ROI_BWD2_EVICT_FIRST", 0);
     v.bwd_sweep3 = env_int("UNIT_ROI_BWD_SWEEP3", 1);
     return v;
   }();

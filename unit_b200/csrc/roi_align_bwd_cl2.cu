@@ -245,8 +245,8 @@ __device__ __forceinline__ void sweep_step(f2& c0, f2& c1, char*& cell, float2 e
       "@q bra.uni SWEEP_NEXT;\n"
 #ifndef UNIT_BWD_NORED
       "mov.b64 {ra, rb}, %0;\n"
-#ifdef UNIT_BWD2_RED_HINT
-      "red.global.add.L2::cache_hint.v2.f32 [%2], {ra, rb}, %7;\n"
+#ifndef UNIT_BWD2_NO_RED_HINT
+      "red.global.add.L2::cache_hint.v2.f32 [%2], {ra, rb}, %7;\n"  // evict_last: the image outlives the tile stream
 #else
       "red.global.add.v2.f32 [%2], {ra, rb};\n"
 #endif
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(NT, 1) roi_align_bwd_cl2(const __grid_constant
   uint64_t policy;
   if (p.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
   else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(policy));
-  uint64_t red_policy;  // experiment (-DUNIT_BWD2_RED_HINT): keep the 34 MB gradient image resident against the stream
+  uint64_t red_policy;  // the 34 MB gradient image stays resident (evict_last) against the 0.8 GB tile stream
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(red_policy));
   if (lane == 0) {
     for (int b = 0; b < NST; ++b) mbar_init(&wa->bar[b], 1);
@@ -475,7 +475,9 @@ int launch_bwd_cl2(const void* gout, const float* rois, void* gfeat, void* ws, i
   p.scale = scale;
   p.sampling_ratio = sr;
   p.aligned = aligned;
-  p.evict_first = switches().bwd_evict_first;
+  // tiles: evict_normal, so the 64-byte DRAM granules two neighbouring tiles share are fetched once (with the image
+  // pinned by the reductions' evict_last hint): DRAM read 1.17 GB -> 0.94 GB, same time (profiles/r02_roi_align_bwd.md)
+  p.evict_first = switches().bwd2_evict_first;
   bwd_tables_kernel<<<cdiv(R, 4), 128, 0, st>>>(rois, tabs, R, N, H, W, scale, sr, aligned);
   UNIT_CHECK_LAUNCH("bwd_tables_kernel");
   launch_bwd_cl_zero(ws, total / 4 + 16, st);

@@ -607,8 +607,12 @@ __global__ void __launch_bounds__(256) mask_paste_window4_kernel(const float* __
     y_lo = max(0, (int)floorf(bx.y - my - 0.5f));
     y_hi = min(H - 1, (int)ceilf(bx.w + my - 0.5f));
   }
-  const int r0 = max(y_lo, (int)blockIdx.x * WIN_ROWS), r1 = min(y_hi, (int)blockIdx.x * WIN_ROWS + WIN_ROWS - 1);
-  if (r0 > r1 || x_lo > x_hi) return;
+  // blockIdx.x = one of gridDim.x equal segments of THIS detection's window rows: every CTA has work (a grid over the
+  // image's row strips launched ~10 000 CTAs of which 95 % exited at once -- their launch cost was the kernel's time)
+  if (y_lo > y_hi || x_lo > x_hi) return;
+  const int rows = y_hi - y_lo + 1, per = (rows + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int r0 = y_lo + (int)blockIdx.x * per, r1 = min(y_hi, r0 + per - 1);
+  if (r0 > r1) return;
   const float* mk = masks + (long long)d * M * M;
   uint32_t* dst = reinterpret_cast<uint32_t*>(out + (long long)d * H * W);
   const int nw = ((x_hi - x_lo) >> 2) + 2;  // words per row, upper bound
@@ -774,8 +778,8 @@ int unit_mask_paste(const float* masks, const float* boxes, int D, int M, int im
     UNIT_CUDA(cudaMemsetAsync(out, 0, (size_t)total, (cudaStream_t)stream));
     dim3 grid(cdiv(img_h, unit::transfer::WIN_ROWS), D);
     if (((long long)img_h * img_w) % 4 == 0 && (((uintptr_t)out) & 3) == 0 && img_w >= 8)
-      mask_paste_window4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(masks, (const float4*)boxes, M, img_h, img_w,
-                                                                        threshold, out);
+      mask_paste_window4_kernel<<<dim3(8, D), 256, 0, (cudaStream_t)stream>>>(masks, (const float4*)boxes, M, img_h,
+                                                                              img_w, threshold, out);
     else
       mask_paste_window_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(masks, (const float4*)boxes, M, img_h, img_w,
                                                                        threshold, out);
