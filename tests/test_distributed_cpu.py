@@ -19,7 +19,8 @@ def _free_port():
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from unit_b200.distributed import FlatGradBucket, gather_detections, shard_indices
+    from unit_b200.distributed import (FlatGradBucket, gather_detection_store, gather_detections, pack_detections,
+                                       shard_indices, unpack_detections)
 
     torch.manual_seed(0)
     lin1, lin2 = torch.nn.Linear(8, 5), torch.nn.Linear(8, 12)
@@ -41,6 +42,12 @@ def _worker(rank, world, port, out):
     b, s, c, n = gather_detections(boxes, scores, classes, counts, topk)
     ok &= len(b) == world and b[1].eq(1).all().item() and c[1].eq(1).all().item() and n[1].tolist() == [2, 2]
     ok &= shard_indices(5, rank, world) == ([0, 2, 4] if rank == 0 else [1, 3])
+    # end-of-loop gather of a rank's whole result store (the reference's single comm.gather)
+    store = torch.cat([pack_detections(boxes, scores, classes, counts) for _ in range(3)])  # 3 steps x 2 images
+    allr = gather_detection_store(store)
+    ok &= tuple(allr.shape) == (world, 6, 6 * topk + 1)
+    ub, us, uc, un = unpack_detections(allr[1], topk)
+    ok &= ub.eq(1).all().item() and uc.eq(1).all().item() and un.tolist() == [2, 2] * 3 and gather_detection_store(store)[0, 0, -1].item() == 1 and us.eq(1.5).all().item()
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -105,3 +105,30 @@ def gather_detections(boxes: torch.Tensor, scores: torch.Tensor, classes: torch.
         c.append(t[:, 5 * topk:6 * topk].to(torch.int64))
         n.append(t[:, 6 * topk].to(torch.int32))
     return b, s, c, n
+
+
+def pack_detections(boxes: torch.Tensor, scores: torch.Tensor, classes: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """Padded detections of n images as ONE [n, 6 * topk + 1] fp32 tensor (boxes | scores | classes | count): what a rank
+    appends to its result store after every inference step and what ``gather_detection_store`` exchanges."""
+    return torch.cat([boxes.reshape(boxes.shape[0], -1), scores, classes.to(scores.dtype),
+                      counts.to(scores.dtype)[:, None]], dim=1)
+
+
+def unpack_detections(packed: torch.Tensor, topk: int):
+    """Inverse of ``pack_detections``: (boxes [n,topk,4], scores [n,topk], classes int64 [n,topk], counts int32 [n])."""
+    return (packed[:, :4 * topk].reshape(-1, topk, 4), packed[:, 4 * topk:5 * topk],
+            packed[:, 5 * topk:6 * topk].to(torch.int64), packed[:, 6 * topk].to(torch.int32))
+
+
+def gather_detection_store(store: torch.Tensor) -> torch.Tensor:
+    """The reference gathers the per-rank prediction lists ONCE, after the inference loop (data/evaluators.py:159,
+    ``comm.gather`` inside ``evaluate()``).  Here every rank keeps its packed detections in one device tensor
+    ``store [n_local_images, 6 * topk + 1]`` and this is that single exchange: one all-gather over NCCL (gloo on CPU)
+    -> [world, n_local_images, 6 * topk + 1] on every rank.  All ranks must hold the same n_local_images."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return store.unsqueeze(0)
+    store = store.contiguous()
+    world = dist.get_world_size()
+    out = torch.empty((world * store.shape[0],) + tuple(store.shape[1:]), dtype=store.dtype, device=store.device)
+    dist.all_gather_into_tensor(out, store)  # concatenated along dim 0 (the form gloo and NCCL both accept)
+    return out.view((world,) + tuple(store.shape))

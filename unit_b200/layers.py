@@ -243,6 +243,9 @@ def draw_permutations(counts_h: Sequence[Sequence[int]], batch_size_per_image: i
     return d
 
 
+_ROW_OFF_CACHE: dict = {}
+
+
 def sample_from_draw(lm: LabelMatch, draw: SampleDraw, devbuf: torch.Tensor, proposals: List[Instances],
                      targets: List[Instances], want_vals: bool = False):
     """Phase 3: one gather launch + the Instances the reference's ``label_and_sample_proposals`` returns."""
@@ -259,6 +262,28 @@ def sample_from_draw(lm: LabelMatch, draw: SampleDraw, devbuf: torch.Tensor, pro
     out, matched_list, vals_list = [], [], []
     off = 0
     num_fg, num_bg = [], []
+    # pass-through proposal fields (objectness_logits ...): for more than two images ONE gather per field over the
+    # concatenated field (global row = sampled row + the image's proposal offset) instead of one launch per image
+    extra = [n for n in proposals[0].get_fields() if n != "proposal_boxes"] if proposals else []
+    batched = {}
+    if n_img > 2 and extra:
+        per_img = [(pso[i + 1] - pso[i]) + (nso[i + 1] - nso[i]) for i in range(n_img)]
+        starts, acc = [], 0
+        for c in lm.prop_counts:
+            starts.append(acc)
+            acc += c
+        key = (tuple(per_img), tuple(lm.prop_counts), str(sampled.device))
+        row_off = _ROW_OFF_CACHE.get(key)
+        if row_off is None:
+            if len(_ROW_OFF_CACHE) > 64:
+                _ROW_OFF_CACHE.clear()
+            row_off = torch.repeat_interleave(torch.tensor(starts, dtype=torch.int64),
+                                              torch.tensor(per_img, dtype=torch.int64)).to(sampled.device)
+            if not ops._is_fake(row_off):
+                _ROW_OFF_CACHE[key] = row_off
+        gidx = sampled + row_off
+        for name in extra:
+            batched[name] = cat([p.get(name) for p in proposals])[gidx]
     for i, (p, t) in enumerate(zip(proposals, targets)):
         n = (pso[i + 1] - pso[i]) + (nso[i + 1] - nso[i])
         sl = slice(off, off + n)
@@ -267,7 +292,7 @@ def sample_from_draw(lm: LabelMatch, draw: SampleDraw, devbuf: torch.Tensor, pro
         res.proposal_boxes = Boxes(s_boxes[sl])
         for name, value in p.get_fields().items():
             if name != "proposal_boxes":
-                res.set(name, value[idx])
+                res.set(name, batched[name][sl] if name in batched else value[idx])
         res.gt_classes = s_classes[sl]
         if lm.gt_counts[i] > 0:
             for name, value in t.get_fields().items():
