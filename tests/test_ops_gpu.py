@@ -619,6 +619,53 @@ def test_mask_paste_full_size(ops):
     assert mism <= 1e-5 * want.numel(), f"{mism} mismatching pixels of {want.numel()}"
 
 
+def _paste_cases():
+    g = seeded(96)
+    cases = []
+    for (D, M, H, W) in ((9, 28, 61, 83), (6, 7, 29, 37), (5, 14, 40, 64)):
+        masks = torch.rand(D, M, M, generator=g)
+        boxes = random_boxes(D, H, W, g, 3.0)
+        boxes[0] = torch.tensor([-7.5, -3.25, W + 9.0, H + 4.5])     # larger than the canvas
+        boxes[1] = torch.tensor([W - 2.5, H - 1.75, W + 6.0, H + 8.0])  # mostly outside
+        boxes[2] = torch.tensor([5.2, 6.1, 5.9, 6.6])                 # smaller than a pixel
+        boxes[3] = torch.tensor([10.0, 4.0, 10.0, 9.0])               # empty (zero width): irregular path
+        boxes[4] = torch.tensor([0.0, 0.0, float(W), float(H)])       # exactly the canvas
+        cases.append((masks, boxes, H, W))
+    return cases
+
+
+def test_mask_paste_edge_cases(ops):
+    """Separable single-pass paste (mask_paste_rows_kernel): odd widths (unaligned heads / tails of every strip), boxes
+    outside / larger than / smaller than a pixel, an empty box, several mask sizes -- against the oracle's
+    paste_masks_in_image, and byte-for-byte against the library's flat per-pixel kernel (UNIT_PASTE_FLAT=1, run in a
+    second process because the switch is read once)."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+
+    from oracle.d2.ops import paste_masks_in_image
+
+    cases = _paste_cases()
+    got = [ops.mask_paste(m.cuda(), b.cuda(), (H, W), 0.5).cpu() for m, b, H, W in cases]
+    for (m, b, H, W), o in zip(cases, got):
+        keep = [i for i in range(b.shape[0]) if i != 3]  # the oracle divides by the zero width
+        want = paste_masks_in_image(m[keep], b[keep], (H, W), 0.5)
+        mism = (o[keep] != want).sum().item()
+        assert mism <= 1e-4 * want.numel(), f"{mism} mismatching pixels of {want.numel()} at {(H, W)}"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "flat.pt")
+        code = ("import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r); from unit_b200 import ops; "
+                "from test_ops_gpu import _paste_cases; "
+                "torch.save([ops.mask_paste(m.cuda(), b.cuda(), (H, W), 0.5).cpu() for m, b, H, W in _paste_cases()], %r)"
+                % (root, os.path.join(root, "tests"), path))
+        subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, UNIT_PASTE_FLAT="1"), timeout=300)
+        flat = torch.load(path)
+    for o, f in zip(got, flat):
+        assert torch.equal(o, f), "separable paste differs from the per-pixel kernel"
+
+
 def test_fused_fastrcnn_loss_and_grads(ops):
     """[D2] FastRCNNOutputs.losses (CE mean + smooth-L1 on get_deltas / R) and its autograd, fused in one kernel."""
     import torch.nn.functional as F

@@ -185,6 +185,8 @@ bwd_tables_kernel(const float* __restrict__ rois, RoiTab* __restrict__ tabs, int
     bool jump = build_axis(g.start_w, g.bin_w, g.gw, W, 1.f / g.count, t->xt, &t->x0, lane);
     jump |= build_axis(g.start_h, g.bin_h, g.gh, H, 1.f, t->yt, &t->y0, lane);
     if (__any_sync(0xffffffffu, jump)) mode = 2;
+    // closing y entry: zero weights + F_ADV, so the row that only received upper taps is swept inside the sample loop
+    if (lane == 0) t->yt[P * g.gh] = make_float2(__uint_as_float(F_ADV), 0.f);
   }
   if (lane == 0) {
     t->mode = mode;
@@ -259,6 +261,58 @@ __device__ __forceinline__ void sweep_step(f2& c0, f2& c1, char*& cell, float2 e
       : "+l"(c0), "+l"(c1), "+l"(cell)
       : "f"(e.x), "f"(e.y), "l"(v), "l"(cstep), "l"(red_policy)
       : "memory");
+}
+
+// The same step for the fully unrolled sweeps.  No "memory" clobber: the reduction targets an image this kernel never
+// reads, and without the clobber the table loads of later samples are hoisted over the block (the loop form prefetches
+// one entry by hand and pays two register moves per sample for it).
+__device__ __forceinline__ void sweep_step_u(f2& c0, f2& c1, char*& cell, float2 e, f2 v, long long cstep,
+                                             uint64_t red_policy) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      ".reg .b64 eh, el;\n"
+      ".reg .b32 fl;\n"
+      ".reg .f32 ra, rb;\n"
+      "mov.b64 eh, {%3, %3};\n"
+      "mov.b64 el, {%4, %4};\n"
+      "fma.rn.f32x2 %0, eh, %5, %0;\n"
+      "fma.rn.f32x2 %1, el, %5, %1;\n"
+      "mov.b32 fl, %3;\n"
+      "and.b32 fl, fl, 1;\n"
+      "setp.eq.u32 q, fl, 0;\n"
+      "@q bra.uni SWEEP_NEXT_U;\n"
+#ifndef UNIT_BWD_NORED
+      "mov.b64 {ra, rb}, %0;\n"
+#ifndef UNIT_BWD2_NO_RED_HINT
+      "red.global.add.L2::cache_hint.v2.f32 [%2], {ra, rb}, %7;\n"
+#else
+      "red.global.add.v2.f32 [%2], {ra, rb};\n"
+#endif
+#endif
+      "add.s64 %2, %2, %6;\n"
+      "mov.b64 %0, %1;\n"
+      "mov.b64 %1, 0;\n"
+      "SWEEP_NEXT_U:\n"
+      "}\n"
+      : "+l"(c0), "+l"(c1), "+l"(cell)
+      : "f"(e.x), "f"(e.y), "l"(v), "l"(cstep), "l"(red_policy));
+}
+
+// Sweep with a compile-time sample count per bin (gw = 1: RoIs up to 224 px wide, gw = 2: up to 448 px): straight-line
+// code, table entries at constant offsets.
+template <int GW>
+__device__ __forceinline__ void sweep_t(const float2* __restrict__ xt, const f2 (&v)[P], char* cell, long long cstep,
+                                        uint64_t red_policy) {
+  f2 c0 = 0ull, c1 = 0ull;
+#pragma unroll
+  for (int pw = 0; pw < P; ++pw) {
+#pragma unroll
+    for (int ix = 0; ix < GW; ++ix) sweep_step_u(c0, c1, cell, xt[pw * GW + ix], v[pw], cstep, red_policy);
+  }
+#ifndef UNIT_BWD_NORED
+  red2(cell, c0);  // the column that only received upper taps
+#endif
 }
 
 // Horizontal sweep of one finished feature row: v[pw] (two channels per lane) is spread over the row's cells with a
@@ -371,15 +425,18 @@ __global__ void __launch_bounds__(NT, 1) roi_align_bwd_cl2(const __grid_constant
           __syncwarp();  // every lane is done with the tile: refill the buffer NST tiles ahead in the stream
           if (lane == 0) refill(cur, nxt, ph / CHUNK_ROWS, b);
         }
+        const int nsb = gh + (ph == P - 1 ? 1 : 0);  // the last bin also takes the closing entry of the y-table
 #pragma unroll 1
-        for (int i = 0; i < gh; ++i) {
+        for (int i = 0; i < nsb; ++i) {
           const float2 e = en;
           en = *++yt;
           const f2 hy = pack2(e.x, e.x), ly = pack2(e.y, e.y);
 #pragma unroll
           for (int pw = 0; pw < P; ++pw) fma2(vlo[pw], hy, g2[pw]);
           if (__float_as_uint(e.x) & F_ADV) {  // last sample whose lower tap is this feature row: sweep it
-            sweep(xt, vlo, rowp, cstep, gw, red_policy);
+            if (gw == 1) sweep_t<1>(xt, vlo, rowp, cstep, red_policy);
+            else if (gw == 2) sweep_t<2>(xt, vlo, rowp, cstep, red_policy);
+            else sweep(xt, vlo, rowp, cstep, gw, red_policy);
             rowp += rstep;
 #pragma unroll
             for (int pw = 0; pw < P; ++pw) {
@@ -392,7 +449,6 @@ __global__ void __launch_bounds__(NT, 1) roi_align_bwd_cl2(const __grid_constant
           }
         }
       }
-      sweep(xt, vlo, rowp, cstep, gw, red_policy);  // the row that only received upper taps
     } else {
       // degenerate / foreign RoIs (mode 0) only drain their tiles; mode 2 evaluates every tap directly
 #pragma unroll 1

@@ -588,55 +588,115 @@ __global__ void __launch_bounds__(256) mask_paste_window_kernel(const float* __r
   }
 }
 
-// Same windows, four pixels per thread: the canvas of one detection is H * W bytes with H * W % 4 == 0, so it is a
-// whole number of aligned 32-bit words; a thread evaluates the 4 pixels of one word (a word may begin up to 3 pixels
-// before the window's first column, or run into the next image row -- every pixel is evaluated at its own (y, x), so a
-// word shared by two rows of the window is written twice with identical contents) and issues ONE 4-byte store: a warp
-// writes 128 contiguous bytes instead of 32.
-__global__ void __launch_bounds__(256) mask_paste_window4_kernel(const float* __restrict__ masks,
-                                                                 const float4* __restrict__ boxes, int M, int H, int W,
-                                                                 float thr, uint8_t* __restrict__ out) {
+// Separable single-pass paste for thr > 0: ONE launch writes the whole canvas with 8-byte stores (no memset node).
+// grid_sample's coordinate chain depends on x only (column) or y only (row), so a CTA = (detection, strip of rows)
+// evaluates it once per window column / strip row into shared-memory tables -- (x0, w, e, inside) and (y0, n, s,
+// inside), the very values paste_sample computes per pixel, from the same rounded operations -- and a pixel costs one
+// table read, four reads of the zero-bordered mask copy and the reference's product / sum order.  Pixels outside the
+// window are written as zeros by the same threads.  Irregular boxes (empty, non-finite, huge) take paste_pixel per byte.
+struct __align__(16) PasteCol {
+  int x0;  // padded column index of the west tap (x0 + 2, clamped into the bordered copy)
+  float w, e;
+  int ok;  // |gx| < 1 + 2 / M
+};
+constexpr int PASTE_STRIP = 32;  // canvas rows per CTA
+constexpr int PASTE_PXT = 8;     // pixels per thread and store
+
+__global__ void __launch_bounds__(256) mask_paste_rows_kernel(const float* __restrict__ masks,
+                                                              const float4* __restrict__ boxes, int M, int H, int W,
+                                                              float thr, uint8_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char paste_smem[];
+  PasteCol* col = reinterpret_cast<PasteCol*>(paste_smem);       // [W], filled for the window columns only
+  PasteCol* rowt = col + W;                                      // [PASTE_STRIP]: (y0, n, s, ok) of the strip's rows
+  float* mb = reinterpret_cast<float*>(rowt + PASTE_STRIP);      // [(M + 4)^2] mask with a 2-pixel zero border
+  const int MP = M + 4;
   const int d = blockIdx.y;
+  const int r0 = blockIdx.x * PASTE_STRIP, r1 = min(H, r0 + PASTE_STRIP);  // rows [r0, r1)
   const float4 bx = __ldg(boxes + d);
-  const float bw = bx.z - bx.x, bh = bx.w - bx.y;
-  int x_lo = 0, x_hi = W - 1, y_lo = 0, y_hi = H - 1;
-  if (bw > 0.f && bh > 0.f && bw < 1e6f && bh < 1e6f && fabsf(bx.x) < 1e6f && fabsf(bx.y) < 1e6f) {
-    const float mx = bw / (float)M + 1.f, my = bh / (float)M + 1.f;
-    x_lo = max(0, (int)floorf(bx.x - mx - 0.5f));
-    x_hi = min(W - 1, (int)ceilf(bx.z + mx - 0.5f));
-    y_lo = max(0, (int)floorf(bx.y - my - 0.5f));
-    y_hi = min(H - 1, (int)ceilf(bx.w + my - 0.5f));
-  }
-  // blockIdx.x = one of gridDim.x equal segments of THIS detection's window rows: every CTA has work (a grid over the
-  // image's row strips launched ~10 000 CTAs of which 95 % exited at once -- their launch cost was the kernel's time)
-  if (y_lo > y_hi || x_lo > x_hi) return;
-  const int rows = y_hi - y_lo + 1, per = (rows + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int r0 = y_lo + (int)blockIdx.x * per, r1 = min(y_hi, r0 + per - 1);
-  if (r0 > r1) return;
+  const float bw = __fsub_rn(bx.z, bx.x), bh = __fsub_rn(bx.w, bx.y);
   const float* mk = masks + (long long)d * M * M;
-  uint32_t* dst = reinterpret_cast<uint32_t*>(out + (long long)d * H * W);
-  const int nw = ((x_hi - x_lo) >> 2) + 2;  // words per row, upper bound
-  const int n = (r1 - r0 + 1) * nw;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int y = r0 + i / nw, k = i - (i / nw) * nw;
-    const int first = (y * W + x_lo) >> 2, last = (y * W + x_hi) >> 2;
-    const int w = first + k;
-    if (w > last) continue;
-    uint32_t word = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int x = 4 * w + j - y * W, yy = y;
-      if (x < 0) {
-        x += W;
-        --yy;
-      } else if (x >= W) {
-        x -= W;
-        ++yy;
-      }
-      if (yy >= y_lo && yy <= y_hi && x >= x_lo && x <= x_hi)
-        word |= (uint32_t)paste_pixel(mk, M, bx, x, yy, thr) << (8 * j);
+  uint8_t* dst = out + (long long)d * H * W;
+  const int a = r0 * W, b = r1 * W;  // this CTA's bytes of the detection's canvas
+  const bool regular = bw > 0.f && bh > 0.f && bw < 1e6f && bh < 1e6f && fabsf(bx.x) < 1e6f && fabsf(bx.y) < 1e6f;
+  if (!regular) {
+    for (int f = a + (int)threadIdx.x; f < b; f += blockDim.x) {
+      const int y = f / W;
+      dst[f] = paste_pixel(mk, M, bx, f - y * W, y, thr);
     }
-    dst[w] = word;
+    return;
+  }
+  // a pixel is sampled only when its centre is within bw / M (bh / M) of the box; + 1 pixel covers all rounding
+  const float mx = bw / (float)M + 1.f, my = bh / (float)M + 1.f;
+  const int x_lo = max(0, (int)floorf(bx.x - mx - 0.5f)), x_hi = min(W - 1, (int)ceilf(bx.z + mx - 0.5f));
+  const int y_lo = max(r0, (int)floorf(bx.y - my - 0.5f)), y_hi = min(r1 - 1, (int)ceilf(bx.w + my - 0.5f));
+  const bool touch = y_lo <= y_hi && x_lo <= x_hi;  // warp-uniform (CTA-uniform)
+  if (touch) {
+    const float lim = 1.f + 2.f / (float)M, half = (float)M * 0.5f;
+    for (int i = threadIdx.x; i < MP * MP; i += blockDim.x) {
+      const int y = i / MP - 2, x = i % MP - 2;
+      mb[i] = (x >= 0 && x < M && y >= 0 && y < M) ? __ldg(mk + y * M + x) : 0.f;
+    }
+    auto entry = [&](float p, float lo, float size) {  // the per-axis part of paste_pixel + paste_sample
+      const float g = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(p, lo), size), 2.f), 1.f);
+      const float i = __fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), half), 0.5f);
+      const float fl = floorf(i);
+      PasteCol c;
+      c.w = __fsub_rn(i, fl);
+      c.e = __fsub_rn(1.f, c.w);
+      c.ok = fabsf(g) < lim;
+      c.x0 = min(max((int)fl + 2, 0), M + 2);  // inside the border whenever ok
+      return c;
+    };
+    for (int x = x_lo + (int)threadIdx.x; x <= x_hi; x += blockDim.x) col[x] = entry((float)x + 0.5f, bx.x, bw);
+    for (int y = y_lo + (int)threadIdx.x; y <= y_hi; y += blockDim.x) {
+      PasteCol c = entry((float)y + 0.5f, bx.y, bh);
+      c.x0 *= MP;
+      rowt[y - r0] = c;
+    }
+    __syncthreads();
+  }
+  auto pixel = [&](int y, int x) -> uint32_t {
+    if (!touch || y < y_lo || y > y_hi || x < x_lo || x > x_hi) return 0u;
+    const PasteCol c = col[x], r = rowt[y - r0];  // r: w = north fraction n, e = s
+    const float* p = mb + r.x0 + c.x0;
+    const float nw = __fmul_rn(p[0], __fmul_rn(r.e, c.e));
+    const float ne = __fmul_rn(p[1], __fmul_rn(r.e, c.w));
+    const float sw = __fmul_rn(p[MP], __fmul_rn(r.w, c.e));
+    const float se = __fmul_rn(p[MP + 1], __fmul_rn(r.w, c.w));
+    const float val = __fadd_rn(__fadd_rn(__fadd_rn(nw, ne), sw), se);
+    return (c.ok && r.ok && val >= thr) ? 1u : 0u;
+  };
+  // bytes [a, b): an unaligned head, 8-byte words, a tail
+  const int head = min(b - a, (int)((8 - ((uintptr_t)(dst + a) & 7)) & 7));
+  const int nwords = (b - a - head) / PASTE_PXT;
+  const int tail0 = a + head + nwords * PASTE_PXT;
+  uint2* words = reinterpret_cast<uint2*>(dst + a + head);
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
+    const int f = a + head + i * PASTE_PXT;
+    int y = f / W, x = f - y * W;
+    uint2 q = make_uint2(0u, 0u);
+    const bool row_in = touch && y >= y_lo && y <= y_hi;
+    if (x + PASTE_PXT > W ? (row_in || (touch && y + 1 >= y_lo && y + 1 <= y_hi)) : (row_in && x <= x_hi && x + PASTE_PXT > x_lo)) {
+#pragma unroll
+      for (int j = 0; j < PASTE_PXT; ++j) {
+        const uint32_t o = pixel(y, x) << (8 * (j & 3));
+        if (j < 4) q.x |= o;
+        else q.y |= o;
+        if (++x == W) {
+          x = 0;
+          ++y;
+        }
+      }
+    }
+    words[i] = q;
+  }
+  if ((int)threadIdx.x < head) {
+    const int f = a + threadIdx.x, y = f / W;
+    dst[f] = (uint8_t)pixel(y, f - y * W);
+  }
+  if (tail0 + (int)threadIdx.x < b) {
+    const int f = tail0 + threadIdx.x, y = f / W;
+    dst[f] = (uint8_t)pixel(y, f - y * W);
   }
 }
 
@@ -774,15 +834,20 @@ int unit_mask_paste(const float* masks, const float* boxes, int D, int M, int im
   UNIT_REQUIRE(masks && boxes && out, "mask_paste: null pointer");
   UNIT_REQUIRE((((uintptr_t)boxes) & 15) == 0, "mask_paste: boxes must be 16-byte aligned");
   const long long total = (long long)D * img_h * img_w;
-  if (threshold > 0.f && D <= 65535 && !switches().paste_flat) {  // outside value is 0: clear, then visit the box windows only
-    UNIT_CUDA(cudaMemsetAsync(out, 0, (size_t)total, (cudaStream_t)stream));
-    dim3 grid(cdiv(img_h, unit::transfer::WIN_ROWS), D);
-    if (((long long)img_h * img_w) % 4 == 0 && (((uintptr_t)out) & 3) == 0 && img_w >= 8)
-      mask_paste_window4_kernel<<<dim3(8, D), 256, 0, (cudaStream_t)stream>>>(masks, (const float4*)boxes, M, img_h,
-                                                                              img_w, threshold, out);
-    else
-      mask_paste_window_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(masks, (const float4*)boxes, M, img_h, img_w,
-                                                                       threshold, out);
+  if (threshold > 0.f && D <= 65535 && !switches().paste_flat) {  // outside value is 0: only the box windows are sampled
+    using namespace unit::transfer;
+    const size_t smem = ((size_t)img_w + PASTE_STRIP) * sizeof(PasteCol) + (size_t)(M + 4) * (M + 4) * sizeof(float);
+    if (smem <= 200 * 1024 && (long long)img_h * img_w < (1ll << 31)) {  // one launch: zero fill + separable sampling
+      if (smem > 48 * 1024)
+        UNIT_CUDA(cudaFuncSetAttribute(mask_paste_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      mask_paste_rows_kernel<<<dim3(cdiv(img_h, PASTE_STRIP), D), 256, smem, (cudaStream_t)stream>>>(
+          masks, (const float4*)boxes, M, img_h, img_w, threshold, out);
+      UNIT_CHECK_LAUNCH("mask_paste_rows_kernel");
+      return UNIT_OK;
+    }
+    UNIT_CUDA(cudaMemsetAsync(out, 0, (size_t)total, (cudaStream_t)stream));  // very wide canvases: memset + windows
+    mask_paste_window_kernel<<<dim3(cdiv(img_h, WIN_ROWS), D), 256, 0, (cudaStream_t)stream>>>(
+        masks, (const float4*)boxes, M, img_h, img_w, threshold, out);
     UNIT_CHECK_LAUNCH("mask_paste_window_kernel");
     return UNIT_OK;
   }
