@@ -599,15 +599,23 @@ struct __align__(16) PasteCol {
   float w, e;
   int ok;  // |gx| < 1 + 2 / M
 };
-constexpr int PASTE_STRIP = 32;  // canvas rows per CTA
+#ifndef UNIT_PASTE_STRIP
+#define UNIT_PASTE_STRIP 32
+#endif
+constexpr int PASTE_STRIP = UNIT_PASTE_STRIP;  // canvas rows per CTA
 constexpr int PASTE_PXT = 8;     // pixels per thread and store
+// Column x lives in slot x ^ ((x >> 3) & 7): neighbouring lanes read columns 8 apart (16-byte entries, 128 bytes = all
+// 32 banks apart -- an 8-way conflict in every quarter-warp phase of the LDS.128); the swizzle spreads them over the 8
+// bank groups.  A slot stays inside its aligned group of 8, so the table is W rounded up to 8 entries.
+__device__ __forceinline__ int paste_slot(int x) { return x ^ ((x >> 3) & 7); }
+__host__ __device__ __forceinline__ int paste_cols(int W) { return (W + 7) & ~7; }
 
 __global__ void __launch_bounds__(256) mask_paste_rows_kernel(const float* __restrict__ masks,
                                                               const float4* __restrict__ boxes, int M, int H, int W,
                                                               float thr, uint8_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char paste_smem[];
-  PasteCol* col = reinterpret_cast<PasteCol*>(paste_smem);       // [W], filled for the window columns only
-  PasteCol* rowt = col + W;                                      // [PASTE_STRIP]: (y0, n, s, ok) of the strip's rows
+  PasteCol* col = reinterpret_cast<PasteCol*>(paste_smem);       // [paste_cols(W)] swizzled, window columns only
+  PasteCol* rowt = col + paste_cols(W);                          // [PASTE_STRIP]: (y0, n, s, ok) of the strip's rows
   float* mb = reinterpret_cast<float*>(rowt + PASTE_STRIP);      // [(M + 4)^2] mask with a 2-pixel zero border
   const int MP = M + 4;
   const int d = blockIdx.y;
@@ -647,7 +655,7 @@ __global__ void __launch_bounds__(256) mask_paste_rows_kernel(const float* __res
       c.x0 = min(max((int)fl + 2, 0), M + 2);  // inside the border whenever ok
       return c;
     };
-    for (int x = x_lo + (int)threadIdx.x; x <= x_hi; x += blockDim.x) col[x] = entry((float)x + 0.5f, bx.x, bw);
+    for (int x = x_lo + (int)threadIdx.x; x <= x_hi; x += blockDim.x) col[paste_slot(x)] = entry((float)x + 0.5f, bx.x, bw);
     for (int y = y_lo + (int)threadIdx.x; y <= y_hi; y += blockDim.x) {
       PasteCol c = entry((float)y + 0.5f, bx.y, bh);
       c.x0 *= MP;
@@ -657,7 +665,7 @@ __global__ void __launch_bounds__(256) mask_paste_rows_kernel(const float* __res
   }
   auto pixel = [&](int y, int x) -> uint32_t {
     if (!touch || y < y_lo || y > y_hi || x < x_lo || x > x_hi) return 0u;
-    const PasteCol c = col[x], r = rowt[y - r0];  // r: w = north fraction n, e = s
+    const PasteCol c = col[paste_slot(x)], r = rowt[y - r0];  // r: w = north fraction n, e = s
     const float* p = mb + r.x0 + c.x0;
     const float nw = __fmul_rn(p[0], __fmul_rn(r.e, c.e));
     const float ne = __fmul_rn(p[1], __fmul_rn(r.e, c.w));
@@ -669,27 +677,11 @@ __global__ void __launch_bounds__(256) mask_paste_rows_kernel(const float* __res
   // bytes [a, b): an unaligned head, 8-byte words, a tail
   const int head = min(b - a, (int)((8 - ((uintptr_t)(dst + a) & 7)) & 7));
   const int nwords = (b - a - head) / PASTE_PXT;
-  const int tail0 = a + head + nwords * PASTE_PXT;
-  uint2* words = reinterpret_cast<uint2*>(dst + a + head);
-  for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
-    const int f = a + head + i * PASTE_PXT;
-    int y = f / W, x = f - y * W;
-    uint2 q = make_uint2(0u, 0u);
-    const bool row_in = touch && y >= y_lo && y <= y_hi;
-    if (x + PASTE_PXT > W ? (row_in || (touch && y + 1 >= y_lo && y + 1 <= y_hi)) : (row_in && x <= x_hi && x + PASTE_PXT > x_lo)) {
-#pragma unroll
-      for (int j = 0; j < PASTE_PXT; ++j) {
-        const uint32_t o = pixel(y, x) << (8 * (j & 3));
-        if (j < 4) q.x |= o;
-        else q.y |= o;
-        if (++x == W) {
-          x = 0;
-          ++y;
-        }
-      }
-    }
-    words[i] = q;
-  }
+  const int w0 = a + head;  // canvas byte of word 0
+  const int tail0 = w0 + nwords * PASTE_PXT;
+  uint2* words = reinterpret_cast<uint2*>(dst + w0);
+  // phase 1: clear the strip (dense 8-byte stores)
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) words[i] = make_uint2(0u, 0u);
   if ((int)threadIdx.x < head) {
     const int f = a + threadIdx.x, y = f / W;
     dst[f] = (uint8_t)pixel(y, f - y * W);
@@ -697,6 +689,58 @@ __global__ void __launch_bounds__(256) mask_paste_rows_kernel(const float* __res
   if (tail0 + (int)threadIdx.x < b) {
     const int f = tail0 + threadIdx.x, y = f / W;
     dst[f] = (uint8_t)pixel(y, f - y * W);
+  }
+  if (!touch) return;
+  __syncthreads();  // the window words below overwrite zeros written by other threads of this CTA
+  // phase 2: the words that hold window pixels, threads packed densely over (window row, word of that row)
+  const int nwr = ((x_hi - x_lo) >> 3) + 2;  // words per window row, upper bound
+  const int total = (y_hi - y_lo + 1) * nwr;
+  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    const int yr = t / nwr, y = y_lo + yr;
+    const int f_lo = y * W + x_lo - w0, f_hi = y * W + x_hi - w0;  // the row's window bytes relative to word 0
+    const int wi = max(f_lo, 0) / PASTE_PXT + (t - yr * nwr);
+    if (f_hi < 0 || wi > min(f_hi / PASTE_PXT, nwords - 1)) continue;
+    int x = wi * PASTE_PXT + w0 - y * W;  // column of the word's first pixel on row y (may lie before the row)
+    uint2 q = make_uint2(0u, 0u);
+    if (x >= 0 && x + PASTE_PXT <= W) {
+      // one row: one row entry; column entries clamped into the window, pixels outside it masked
+      const PasteCol r = rowt[y - r0];
+      const float* mrow = mb + r.x0;
+#pragma unroll
+      for (int j = 0; j < PASTE_PXT; ++j) {
+        const int xj = x + j;
+        const PasteCol c = col[paste_slot(min(max(xj, x_lo), x_hi))];
+        const float* p = mrow + c.x0;
+        const float nw = __fmul_rn(p[0], __fmul_rn(r.e, c.e));
+        const float ne = __fmul_rn(p[1], __fmul_rn(r.e, c.w));
+        const float sw = __fmul_rn(p[MP], __fmul_rn(r.w, c.e));
+        const float se = __fmul_rn(p[MP + 1], __fmul_rn(r.w, c.w));
+        const float val = __fadd_rn(__fadd_rn(__fadd_rn(nw, ne), sw), se);
+        const bool on = xj >= x_lo && xj <= x_hi && (c.ok & r.ok) != 0 && val >= thr;
+        const uint32_t o = on ? (1u << (8 * (j & 3))) : 0u;
+        if (j < 4) q.x |= o;
+        else q.y |= o;
+      }
+    } else {
+      // the word straddles two canvas rows (a window that touches the left / right border): every pixel at its own
+      // (row, column); when both rows are window rows the word is written twice with identical contents
+      int yy = y;
+      if (x < 0) {
+        x += W;
+        --yy;
+      }
+#pragma unroll 1
+      for (int j = 0; j < PASTE_PXT; ++j) {
+        const uint32_t o = pixel(yy, x) << (8 * (j & 3));
+        if (j < 4) q.x |= o;
+        else q.y |= o;
+        if (++x == W) {
+          x = 0;
+          ++yy;
+        }
+      }
+    }
+    words[wi] = q;
   }
 }
 
@@ -836,7 +880,7 @@ int unit_mask_paste(const float* masks, const float* boxes, int D, int M, int im
   const long long total = (long long)D * img_h * img_w;
   if (threshold > 0.f && D <= 65535 && !switches().paste_flat) {  // outside value is 0: only the box windows are sampled
     using namespace unit::transfer;
-    const size_t smem = ((size_t)img_w + PASTE_STRIP) * sizeof(PasteCol) + (size_t)(M + 4) * (M + 4) * sizeof(float);
+    const size_t smem = ((size_t)paste_cols(img_w) + PASTE_STRIP) * sizeof(PasteCol) + (size_t)(M + 4) * (M + 4) * sizeof(float);
     if (smem <= 200 * 1024 && (long long)img_h * img_w < (1ll << 31)) {  // one launch: zero fill + separable sampling
       if (smem > 48 * 1024)
         UNIT_CUDA(cudaFuncSetAttribute(mask_paste_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
