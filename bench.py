@@ -825,13 +825,20 @@ def run_infer(args):
     stage = RoIStage(head, lambda pooled: (x, xw))
     topk = head.box_predictor.test_topk_per_image
     host = []
+    # as in the training arm the res4 features leave the host as bf16 (the dtype BASELINE configs[1] names) and are
+    # widened on the device inside the timed region; --e2e-upload-f32 copies fp32 (twice the PCIe bytes)
+    up_bf16 = not args.e2e_upload_f32
     for s_ in range(N_SETS):
         f, pr, _, _ = make_inputs(3000 + 10 * rank + s_)
+        if up_bf16:
+            f = f.bfloat16()
         host.append((f.pin_memory(), [p[:P_INF].contiguous().pin_memory() for p in pr]))
     dev_sets = []
     for f, pr in host:
-        dev_sets.append((f.to(device), [Instances(IMG_HW, proposal_boxes=Boxes(p.to(device)),
-                                                  objectness_logits=torch.zeros(P_INF, device=device)) for p in pr]))
+        dev_sets.append((f.float().to(device), [Instances(IMG_HW, proposal_boxes=Boxes(p.to(device)),
+                                                          objectness_logits=torch.zeros(P_INF, device=device))
+                                                for p in pr]))
+    stage_bf16 = [torch.empty_like(f, device=device) for f, _ in host] if up_bf16 else None
     copy_stream = torch.cuda.Stream(device=device)
     copied = [torch.cuda.Event() for _ in range(N_SETS)]
     freed = [torch.cuda.Event() for _ in range(N_SETS)]
@@ -884,7 +891,11 @@ def run_infer(args):
         copy_stream.wait_event(freed[k])
         with torch.cuda.stream(copy_stream):
             f, pr = host[k]
-            dev_sets[k][0].copy_(f, non_blocking=True)
+            if up_bf16:
+                stage_bf16[k].copy_(f, non_blocking=True)
+                dev_sets[k][0].copy_(stage_bf16[k])
+            else:
+                dev_sets[k][0].copy_(f, non_blocking=True)
             for inst, src in zip(dev_sets[k][1], pr):
                 inst.proposal_boxes.tensor.copy_(src, non_blocking=True)
             copied[k].record(copy_stream)
@@ -944,7 +955,7 @@ def run_infer(args):
     per_call = _lib.launch_count() - n0
     if rank == 0:
         ms_step = total_ms / args.steps
-        h2d = int(host[0][0].numel() * 4 + sum(p.numel() * 4 for p in host[0][1]))
+        h2d = int(host[0][0].numel() * host[0][0].element_size() + sum(p.numel() * 4 for p in host[0][1]))
         line = {
             "metric": "RoI-stage inference images/sec (VOC R101-C4, 512 proposals/img)",
             "value": world * N_IMG / (ms_step / 1e3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -960,7 +971,8 @@ def run_infer(args):
                                       "detections (reference: data/evaluators.py:159)"},
             "e2e": {"value": world * N_IMG / (e2e_ms / args.steps / 1e3), "unit": "images/s",
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": int(N_IMG * width * 4)},
+                    "d2h_bytes_per_step": int(N_IMG * width * 4),
+                    "upload_dtype": "bf16 features, widened on the device inside the timed region" if up_bf16 else "f32"},
             "gpu_launches": int(per_call * args.steps), "detections_last_step": state["dets"],
             "detections_gathered": state.get("gathered"), "clocks": clocks,
             "gathered_bytes_per_rank": int(args.steps * N_IMG * width * 4),

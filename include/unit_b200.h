@@ -129,7 +129,8 @@ int unit_fastrcnn_loss(const float* scores, const float* deltas, const float* pr
                        float smooth_l1_beta, float* losses, float* d_scores, float* d_deltas, void* workspace,
                        size_t workspace_bytes, unit_stream_t stream);
 /* Same, with both gradients written into ONE packed buffer d_packed[R, ld_packed] = [d_scores (K+1) | d_deltas (4K) |
- * zeros]: the layout unit_predictor_wgrad consumes (ld_packed >= 128 there). */
+ * zeros]: the layout unit_predictor_wgrad consumes (ld_packed >= 128 there).  Here losses has THREE elements:
+ * (loss_cls, loss_box_reg, loss_cls + loss_box_reg) -- the total the trainer logs, without another launch. */
 int unit_fastrcnn_loss_packed(const float* scores, const float* deltas, const float* proposals, const float* gt_boxes,
                               const int64_t* gt_classes, int R, int K, float wx, float wy, float ww, float wh,
                               float smooth_l1_beta, float* losses, float* d_packed, int ld_packed, void* workspace,

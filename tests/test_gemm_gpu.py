@@ -114,7 +114,7 @@ def test_fused_ft_step_matches_modular():
     vs the modular predictor.forward + losses + autograd at the same TF32 precision."""
     import os
     from conftest import ROOT
-    from unit_b200 import d2compat  # noqa: F401
+    from unit_b200 import d2compat, ops  # noqa: F401
     from unit_b200.config import load_cfg
     from unit_b200.registry import ROI_BOX_HEAD_REGISTRY
     from unit_b200.roi_heads import build_roi_heads
@@ -163,6 +163,7 @@ def test_fused_ft_step_matches_modular():
 
     bucket = FlatGradBucket([p for p in fused.parameters() if p.requires_grad])
     lf, _ = fused.box_losses(x, xw, props)
+    assert abs(lf.total.item() - (lf["loss_cls"].item() + lf["loss_box_reg"].item())) < 1e-6  # third output of the launch
     (lf["loss_cls"] + 2.0 * lf["loss_box_reg"]).backward()
     modular.box_predictor.can_fuse_losses = lambda *a, **k: False
     lm, _ = modular.box_losses(x, xw, props)
@@ -175,6 +176,14 @@ def test_fused_ft_step_matches_modular():
         for part in ("weight", "bias"):
             a, b = getattr(getattr(pf, name), part).grad, getattr(getattr(pm, name), part).grad
             assert ((a - b).norm() / b.norm().clamp(min=1e-12)).item() < 1e-2, (name, part)
+    # overwrite_bound_grads: the bucket holds garbage, the backward writes instead of accumulating (RoIStage's path)
+    want = bucket.flat.clone()
+    bucket.flat.fill_(123.0)
+    lf4, _ = fused.box_losses(x, xw, props)
+    one = torch.ones((), device="cuda")
+    with ops.overwrite_bound_grads():
+        torch.autograd.backward([lf4["loss_cls"], lf4["loss_box_reg"]], [one, 2.0 * one])
+    assert torch.allclose(bucket.flat, want, rtol=1e-5, atol=1e-7)
     # no bound buffers: gradients come back through autograd as usual
     fused2 = make()
     lf2, _ = fused2.box_losses(x, xw, props)

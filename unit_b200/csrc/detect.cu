@@ -1204,7 +1204,7 @@ __global__ void row_losses_kernel(const float* __restrict__ scores, const float*
   d_box[(long long)r * 4 + lane] = dv;
 }
 
-__global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int R, float* __restrict__ out) {
+__global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int R, float* __restrict__ out, int with_total) {
   __shared__ float s0[32], s1[32];
   float a = 0.f, b = 0.f;
   for (int i = threadIdx.x; i < R; i += blockDim.x) {
@@ -1228,6 +1228,7 @@ __global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int R, fl
     }
     out[0] = ta / (float)R;
     out[1] = tb / (float)R;
+    if (with_total) out[2] = out[0] + out[1];  // what the trainer sums on the host side of the reference
   }
 }
 
@@ -1244,7 +1245,7 @@ extern "C" int unit_fastrcnn_loss_packed(const float* scores, const float* delta
   UNIT_REQUIRE(ld_packed >= 5 * K + 1, "fastrcnn_loss_packed: row stride smaller than (K+1) + 4K");
   cudaStream_t st = (cudaStream_t)stream;
   if (R == 0) {
-    UNIT_CUDA(cudaMemsetAsync(losses, 0, 2 * sizeof(float), st));
+    UNIT_CUDA(cudaMemsetAsync(losses, 0, 3 * sizeof(float), st));
     return UNIT_OK;
   }
   UNIT_REQUIRE(scores && deltas && proposals && gt_boxes && gt_classes && d_packed, "fastrcnn_loss: null pointer");
@@ -1257,7 +1258,7 @@ extern "C" int unit_fastrcnn_loss_packed(const float* scores, const float* delta
       scores, deltas, (const float4*)proposals, (const float4*)gt_boxes, gt_classes, R, K, wx, wy, ww, wh,
       smooth_l1_beta, (float*)workspace, d_packed, d_packed + (K + 1), ld_packed, ld_packed, ld_packed - (5 * K + 1));
   UNIT_CHECK_LAUNCH("fastrcnn_loss_kernel");
-  unit::detect::loss_reduce_kernel<<<1, 1024, 0, st>>>((const float*)workspace, R, losses);
+  unit::detect::loss_reduce_kernel<<<1, 1024, 0, st>>>((const float*)workspace, R, losses, 1);
   UNIT_CHECK_LAUNCH("loss_reduce_kernel");
   return UNIT_OK;
 }
@@ -1284,7 +1285,7 @@ extern "C" int unit_fastrcnn_loss(const float* scores, const float* deltas, cons
       scores, deltas, (const float4*)proposals, (const float4*)gt_boxes, gt_classes, R, K, wx, wy, ww, wh,
       smooth_l1_beta, (float*)workspace, d_scores, d_deltas, K + 1, 4 * K, 0);
   UNIT_CHECK_LAUNCH("fastrcnn_loss_kernel");
-  unit::detect::loss_reduce_kernel<<<1, 1024, 0, st>>>((const float*)workspace, R, losses);
+  unit::detect::loss_reduce_kernel<<<1, 1024, 0, st>>>((const float*)workspace, R, losses, 0);
   UNIT_CHECK_LAUNCH("loss_reduce_kernel");
   return UNIT_OK;
 }

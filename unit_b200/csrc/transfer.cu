@@ -600,7 +600,7 @@ struct __align__(16) PasteCol {
   int ok;  // |gx| < 1 + 2 / M
 };
 #ifndef UNIT_PASTE_STRIP
-#define UNIT_PASTE_STRIP 32
+#define UNIT_PASTE_STRIP 16
 #endif
 constexpr int PASTE_STRIP = UNIT_PASTE_STRIP;  // canvas rows per CTA
 constexpr int PASTE_PXT = 8;     // pixels per thread and store

@@ -918,13 +918,14 @@ def predictor_wgrad(gy: torch.Tensor, x: torch.Tensor, n_cols: int, seg_rows: Se
 
 def fastrcnn_loss_packed(scores, deltas, proposals, gt_boxes, gt_classes, weights=(10.0, 10.0, 5.0, 5.0), beta=0.0):
     """FastRCNNOutputs.losses with both gradients in one packed, zero-padded buffer:
-    -> (losses [2], d_packed [R, ld] = [dL_cls/dscores | dL_box/ddeltas | 0], ld = multiple of 128)."""
+    -> (losses [3] = (loss_cls, loss_box_reg, their sum), d_packed [R, ld] = [dL_cls/dscores | dL_box/ddeltas | 0],
+    ld = multiple of 128)."""
     dev = _need_cuda(scores, deltas)
     scores, deltas = _c(scores, _F32), _c(deltas, _F32)
     R, K1 = scores.shape
     K = K1 - 1
     ld = (5 * K + 1 + 127) // 128 * 128
-    losses = torch.empty((2,), dtype=_F32, device=dev)
+    losses = torch.empty((3,), dtype=_F32, device=dev)
     d_packed = torch.empty((R, ld), dtype=_F32, device=dev)
     ws = _workspace(dev, max(R, 1) * 8)
     check(lib().unit_fastrcnn_loss_packed(_ptr(scores), _ptr(deltas), _ptr(_c(proposals, _F32)), _ptr(_c(gt_boxes, _F32)),
@@ -958,11 +959,12 @@ class _FTStepLossFn(torch.autograd.Function):
         ctx.params = (cls_w, cls_b, box_w, box_b)
         ctx.K1 = K1
         ctx.n_cols = 5 * spec.K + 1
-        ctx.mark_non_differentiable(scores, bbox)
-        return losses[0], losses[1], scores, bbox
+        total = losses[2]
+        ctx.mark_non_differentiable(scores, bbox, total)
+        return losses[0], losses[1], scores, bbox, total
 
     @staticmethod
-    def backward(ctx, g_cls, g_box, _gs, _gb):
+    def backward(ctx, g_cls, g_box, _gs, _gb, _gt):
         x, d_packed = ctx.saved_tensors
         cls_w, cls_b, box_w, box_b = ctx.params
         params = (cls_w, cls_b, box_w, box_b)
@@ -976,14 +978,33 @@ class _FTStepLossFn(torch.autograd.Function):
             dst = [torch.empty_like(p) if n else None for p, n in zip(params, need)]
             ret = tuple(dst)
         sc = [_c(g_cls.reshape(1), _F32), _c(g_box.reshape(1), _F32)]
+        # overwrite_bound_grads(): the caller guarantees the bound buffers hold nothing to keep (it would have zeroed
+        # them), so the kernel writes instead of accumulating and the zero fill is not needed
         predictor_wgrad(d_packed, x, ctx.n_cols, [0, ctx.K1, ctx.n_cols], [dst[0], dst[2]], [dst[1], dst[3]], sc,
-                        accumulate=bound)
+                        accumulate=bound and not _OVERWRITE_BOUND[0])
         return ret + (None,) * 9
+
+
+_OVERWRITE_BOUND = [False]
+
+
+class overwrite_bound_grads:
+    """Context for ONE backward of the fused fine-tune node: gradients are WRITTEN into the bound ``.grad`` buffers
+    (the flat all-reduce bucket) instead of accumulated, which makes the bucket's zero fill before the step
+    unnecessary.  Only for callers that own the buffers and would have zeroed them (RoIStage)."""
+
+    def __enter__(self):
+        self._prev, _OVERWRITE_BOUND[0] = _OVERWRITE_BOUND[0], True
+        return self
+
+    def __exit__(self, *exc):
+        _OVERWRITE_BOUND[0] = self._prev
+        return False
 
 
 def ft_step_losses(cls_w, cls_b, box_w, box_b, x, xw, pack, spec, proposals, gt_boxes, gt_classes,
                    weights=(10.0, 10.0, 5.0, 5.0), beta=0.0):
-    """-> (loss_cls, loss_box_reg, scores [detached], bbox [detached])."""
+    """-> (loss_cls, loss_box_reg, scores [detached], bbox [detached], loss_cls + loss_box_reg [detached])."""
     return _FTStepLossFn.apply(cls_w, cls_b, box_w, box_b, x, xw, pack, spec, proposals, gt_boxes, gt_classes,
                                tuple(weights), float(beta))
 

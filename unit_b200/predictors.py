@@ -23,6 +23,13 @@ from .structures import Boxes, Instances, ShapeSpec
 logger = logging.getLogger("unit_b200")
 
 
+class LossDict(dict):
+    """The losses dict of the reference (name -> scalar tensor) that may also carry ``total``: the sum of its values
+    computed by the same launch that produced them (fused fine-tune node), so a trainer need not add them again."""
+
+    total: Optional[torch.Tensor] = None
+
+
 def _freeze(module: nn.Module, layers_to_freeze: Sequence[str]) -> None:
     """Freeze by first dotted component of the parameter name (fast_rcnn.py:353-358, roi_heads.py:166-171)."""
     for name, param in module.named_parameters():
@@ -585,16 +592,18 @@ class SupervisedDetectorOutputsFineTune(SupervisedDetectorOutputsBase):
 
     def forward_losses(self, x, x_weak_branch, spec: ops.TransferSpec, proposals):
         """forward (fast_rcnn.py:484-533) + losses (:435-453) for sampled ``proposals`` as ONE autograd node.
-        Returns ({'loss_cls', 'loss_box_reg'}, [scores, bbox]) -- the predictions are detached."""
+        Returns ({'loss_cls', 'loss_box_reg'} as a LossDict carrying .total, [scores, bbox]) -- predictions detached."""
         pk = self._pack()
         gt_classes = layers.cat([p_.gt_classes for p_ in proposals])
         prop = layers.cat([p_.proposal_boxes.tensor for p_ in proposals])
         gt_boxes = layers.cat([p_.gt_boxes.tensor for p_ in proposals])
         xw = x if x_weak_branch is None else x_weak_branch
-        loss_cls, loss_box, scores, bbox = ops.ft_step_losses(
+        loss_cls, loss_box, scores, bbox, total = ops.ft_step_losses(
             self.cls_score_ft.weight, self.cls_score_ft.bias, self.bbox_pred_ft.weight, self.bbox_pred_ft.bias, x, xw, pk,
             spec, prop, gt_boxes, gt_classes, self.box2box_transform.weights, self.smooth_l1_beta)
-        return {"loss_cls": loss_cls, "loss_box_reg": loss_box}, [scores, bbox]
+        losses = LossDict(loss_cls=loss_cls, loss_box_reg=loss_box)
+        losses.total = total  # the sum the trainer would form, from the same launch
+        return losses, [scores, bbox]
 
 
 @FAST_RCNN_REGISTRY.register()

@@ -112,6 +112,7 @@ class RoIStage:
         Returns (loss tensor, dL/dfeatures)."""
         head = self.head
         head.move_mappings_to_gpu()
+        self._seed(features.device)
         sampled = head.label_and_sample_proposals(proposals, targets)
         loss, rois, pooled = self._forward_backward(features, sampled)
         work = self.bucket.all_reduce_mean(async_op=True) if self.bucket is not None else None
@@ -124,8 +125,6 @@ class RoIStage:
         """Sampled RoIs -> ROIAlign fwd -> box head -> transfer -> losses -> backward into the bucket.  Shapes are
         fixed by the sample counts and nothing synchronises (capturable)."""
         head = self.head
-        if self.bucket is not None:
-            self.bucket.zero_()
         boxes = [p.proposal_boxes for p in sampled]
         rois = ops.boxes_to_rois(layers.cat([b.tensor for b in boxes]),
                                  ops.offsets_from_counts([len(b) for b in boxes], features.device))
@@ -134,9 +133,35 @@ class RoIStage:
                                        pool.aligned, True)
         x, xw = self.box_head_fn(pooled)
         losses, _ = head.box_losses(x, xw, sampled)  # ONE fused node in the shipped fine-tune setting
+        total = getattr(losses, "total", None)
+        if total is not None and self._bucket_is_exactly(head.box_predictor):
+            # fused node + a bucket that holds exactly its four gradients: no loss add, no seed fill (persistent ones),
+            # no zero fill of the bucket (the weight-gradient kernel writes instead of accumulating)
+            self.bucket.bind()
+            one = self._seed(total.device)
+            with ops.overwrite_bound_grads():
+                torch.autograd.backward([losses["loss_cls"], losses["loss_box_reg"]], [one, one])
+            return total, rois, pooled
+        if self.bucket is not None:
+            self.bucket.zero_()  # gradients are not touched before this point
         loss = losses["loss_cls"] + losses["loss_box_reg"]
         loss.backward()
         return loss.detach(), rois, pooled
+
+    def _seed(self, device) -> torch.Tensor:
+        one = self.__dict__.get("_one")
+        if one is None or one.device != device:
+            one = self._one = torch.ones((), dtype=torch.float32, device=device)
+        return one
+
+    def _bucket_is_exactly(self, predictor) -> bool:
+        if self.bucket is None:
+            return False
+        want = [getattr(predictor, n, None) for n in ("cls_score_ft", "bbox_pred_ft")]
+        if any(m is None for m in want):
+            return False
+        ids = {id(m.weight) for m in want} | {id(m.bias) for m in want}
+        return {id(p) for p in self.bucket.params} == ids
 
     def _roi_backward(self, features, rois, pooled, grad_pooled_fn):
         if grad_pooled_fn is None:
@@ -160,6 +185,7 @@ class RoIStage:
         the graph's static outputs: they are overwritten by the next replay with the same key."""
         head = self.head
         head.move_mappings_to_gpu()
+        self._seed(features.device)  # created outside any capture
         key = self._step_key(features, proposals, targets)
         st = self._graphs.get(key)
         if st is None:
