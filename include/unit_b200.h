@@ -107,7 +107,17 @@ int unit_sample_gather(const int64_t* pos_idx, const int64_t* neg_idx, const int
                        const int* gt_offsets, int n_img, int S_total, const float* prop_boxes,
                        const int64_t* prop_classes, const int64_t* matches, const float* gt_boxes,
                        int64_t* sampled_idx, float* out_boxes, int64_t* out_classes, int64_t* out_matched,
-                       float* out_gt_boxes, unit_stream_t stream);
+                       float* out_gt_boxes, const float* prop_field, float* out_field, unit_stream_t stream);
+/* prop_field / out_field (both may be NULL): one pass-through float field of the proposals (objectness_logits),
+ * concatenated like prop_boxes, gathered by the same launch: out_field[j] = prop_field[global row of sample j]. */
+
+/* [D2] proposal_utils.add_ground_truth_to_proposals (called at roi_heads.py:459 through label_and_sample_proposals)
+ * for n_img images in one launch per 32 images: out rows of image i = its prop_counts[i] proposals, then its
+ * gt_counts[i] ground-truth boxes with objectness logit gt_logit; images back to back.  prop_boxes / prop_logits /
+ * gt_boxes / prop_counts / gt_counts are HOST arrays of n_img device pointers / counts. */
+int unit_append_gt(const float* const* prop_boxes, const float* const* prop_logits, const float* const* gt_boxes,
+                   const int* prop_counts, const int* gt_counts, int n_img, float gt_logit, float* out_boxes,
+                   float* out_logits, unit_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * softmax + Box2BoxTransform.apply_deltas.  Replaces [D2] FastRCNNOutputLayers.predict_probs / predict_boxes

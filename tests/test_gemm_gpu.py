@@ -109,6 +109,41 @@ def test_predictor_wgrad_tcgen05(R, N, K, accumulate):
     assert torch.allclose(got_b, ref_b, rtol=1e-4, atol=1e-5)
 
 
+def test_tensor_map_entry_from_a_fresh_thread():
+    """A thread whose FIRST CUDA action is a call into the library (an autograd worker running the fused node's
+    backward with no gradient tensors to materialise): cuTensorMapEncodeTiled needs a driver context current on that
+    thread, which ensure_driver_context() binds."""
+    import threading
+
+    from unit_b200 import ops
+
+    g = seeded(5)
+    R, K, N = 256, 512, 101
+    x = torch.randn(R, K, generator=g).cuda()
+    gy = torch.zeros(R, 128).cuda()
+    gy[:, :N] = torch.randn(R, N, generator=g).cuda()
+    w, b, sc = torch.zeros(N, K).cuda(), torch.zeros(N).cuda(), torch.ones(1).cuda()
+    ops.predictor_wgrad(gy, x, N, [0, N], [w], [b], [sc], accumulate=False)  # main thread; sizes the workspace
+    torch.cuda.synchronize()
+    want = w.clone()
+    w.zero_()
+    torch.cuda.synchronize()
+    err = []
+
+    def run():
+        try:
+            ops.predictor_wgrad(gy, x, N, [0, N], [w], [b], [sc], accumulate=False)
+        except Exception as e:  # noqa: BLE001
+            err.append(e)
+
+    t = threading.Thread(target=run)
+    t.start()
+    t.join()
+    torch.cuda.synchronize()
+    assert not err, err
+    assert torch.equal(w, want)
+
+
 def test_fused_ft_step_matches_modular():
     """ops.ft_step_losses (grouped GEMM -> transfer -> packed loss; backward = tcgen05 wgrad into bound .grad buffers)
     vs the modular predictor.forward + losses + autograd at the same TF32 precision."""

@@ -584,6 +584,45 @@ def test_transfer_reads_packed_gemm_outputs_in_place(ops):
     assert torch.equal(f3.grad, f2.grad)
 
 
+def test_append_gt_and_field_gather(ops):
+    """[D2] add_ground_truth_to_proposals as one launch (unit_append_gt) and the objectness_logits gathered by the
+    sampling launch: same tensors as the torch formulation, per-image results are views of one buffer."""
+    import math
+
+    from unit_b200 import layers
+    from unit_b200.structures import Boxes, Instances
+
+    g = seeded(41)
+    props, gts, tgts = [], [], []
+    for n, k in ((37, 3), (0, 2), (50, 0), (64, 5)):
+        pb = random_boxes(n, 480, 640, g, 8.0)
+        gb = random_boxes(k, 480, 640, g, 24.0)
+        props.append(Instances((480, 640), proposal_boxes=Boxes(pb.cuda()),
+                               objectness_logits=torch.randn(n, generator=g).cuda()))
+        gts.append(Boxes(gb.cuda()))
+        tgts.append(Instances((480, 640), gt_boxes=Boxes(gb.cuda()),
+                              gt_classes=torch.randint(0, 20, (k,), generator=g).cuda()))
+    out = layers.add_ground_truth_to_proposals(gts, props)
+    logit = math.log((1.0 - 1e-10) / (1 - (1.0 - 1e-10)))
+    for o, p, gt in zip(out, props, gts):
+        assert torch.equal(o.proposal_boxes.tensor, torch.cat([p.proposal_boxes.tensor, gt.tensor]))
+        want = torch.cat([p.objectness_logits, torch.full((len(gt),), logit, device="cuda")])
+        assert torch.equal(o.objectness_logits, want)
+    allb = layers.cat([o.proposal_boxes.tensor for o in out])
+    assert allb.data_ptr() == out[0].proposal_boxes.tensor.data_ptr() and allb.shape[0] == sum(len(o) for o in out)
+    # sampled proposals carry the logits of the rows they were drawn from
+    gen = torch.Generator().manual_seed(5)
+    sampled, _, _ = layers.label_and_sample(out, tgts, num_classes=20, batch_size_per_image=32, positive_fraction=0.25,
+                                            thresholds=[0.5], labels=[0, 1], generator=gen)
+    for s_, o in zip(sampled, out):
+        if len(s_) == 0:
+            continue
+        eq = (s_.proposal_boxes.tensor[:, None, :] == o.proposal_boxes.tensor[None, :, :]).all(-1)
+        assert eq.any(1).all()
+        src = eq.float().argmax(1)
+        assert torch.equal(s_.objectness_logits, o.objectness_logits[src])
+
+
 # ----------------------------------------------------------------------------------------------- masks
 def test_mask_transfer_and_paste_golden(ops):
     gold = load_golden("mask_head.pt")

@@ -42,7 +42,9 @@ _SIGNATURES = {
                              P]),
     "unit_iou_match": (c_int, [P, P, P, P, c_int, c_int, POINTER(c_float), POINTER(c_int), c_int, P, P, P, P]),
     "unit_label_proposals": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P]),
-    "unit_sample_gather": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, P, P, P]),
+    "unit_sample_gather": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "unit_append_gt": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int),
+                               c_int, c_float, P, P, P]),
     "unit_softmax_decode": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float,
                                     P]),
     "unit_box_get_deltas": (c_int, [P, P, P, c_int, c_float, c_float, c_float, c_float, P]),

@@ -4,6 +4,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace unit {
@@ -31,6 +33,28 @@ int sm_count() {
       cached = 148;
   }
   return cached;
+}
+
+int ensure_driver_context(const void* dev_ptr) {
+  typedef CUresult (*CtxGetCurrentFn)(CUcontext*);
+  static CtxGetCurrentFn get_current = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return (CtxGetCurrentFn)ptr;
+  }();
+  CUcontext ctx = nullptr;
+  if (get_current && get_current(&ctx) == CUDA_SUCCESS && ctx != nullptr) return UNIT_OK;
+  int dev = -1;
+  cudaPointerAttributes attr;
+  if (dev_ptr && cudaPointerGetAttributes(&attr, dev_ptr) == cudaSuccess && attr.type == cudaMemoryTypeDevice)
+    dev = attr.device;
+  (void)cudaGetLastError();  // a host pointer is not an error here
+  if (dev < 0) UNIT_CUDA(cudaGetDevice(&dev));
+  UNIT_CUDA(cudaSetDevice(dev));  // CUDA 12: initialises the runtime and makes the primary context current
+  return UNIT_OK;
 }
 
 static int env_int(const char* name, int dflt) {

@@ -43,6 +43,12 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 int sm_count();
 
+// The driver entry points this library calls (cuTensorMapEncodeTiled) need a context current on the CALLING thread.  A
+// thread that has made no runtime call yet has none -- e.g. a PyTorch autograd worker whose first CUDA action is a
+// call into this library -- and the driver answers CUDA_ERROR_INVALID_CONTEXT.  When no context is current, bind the
+// primary context of the device that owns `dev_ptr` (the device the call is about to launch on).  No effect otherwise.
+int ensure_driver_context(const void* dev_ptr);
+
 // Developer switches (kernel-variant experiments), read from the environment ONCE per process -- never on a launch path.
 struct Switches {
   bool filter_single, nms_single, fwd_band_bf16, fwd_v3, bwd_v4, bwd_cl1, paste_flat;

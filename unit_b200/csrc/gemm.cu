@@ -230,6 +230,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int box_rows) {
+  if (int rc = ensure_driver_context(ptr)) return rc;
   EncodeTiledFn enc = encode_fn();
   UNIT_REQUIRE(enc != nullptr, "predictor_gemm: cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -446,6 +447,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, const flo
 }
 
 static int make_map_mn(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_blocks) {
+  if (int rc = ensure_driver_context(ptr)) return rc;
   EncodeTiledFn enc = encode_fn();
   UNIT_REQUIRE(enc != nullptr, "predictor_wgrad: cuTensorMapEncodeTiled not available from the driver");
   // 3-D view (column within a 32-block, row, 32-block): strides 4 B, ld * 4 B, 128 B

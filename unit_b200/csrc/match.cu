@@ -191,7 +191,8 @@ __global__ void sample_gather_kernel(const int64_t* __restrict__ pos_idx, const 
                                      const int64_t* __restrict__ prop_classes, const int64_t* __restrict__ matches,
                                      const float4* __restrict__ gt_boxes, int64_t* __restrict__ sampled_idx,
                                      float4* __restrict__ out_boxes, int64_t* __restrict__ out_classes,
-                                     int64_t* __restrict__ out_matched, float4* __restrict__ out_gt_boxes) {
+                                     int64_t* __restrict__ out_matched, float4* __restrict__ out_gt_boxes,
+                                     const float* __restrict__ prop_field, float* __restrict__ out_field) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= S_total) return;
   // output rows of image i start at pos_sel_off[i] + neg_sel_off[i]
@@ -211,11 +212,43 @@ __global__ void sample_gather_kernel(const int64_t* __restrict__ pos_idx, const 
   if (sampled_idx) sampled_idx[j] = src;
   if (out_boxes) out_boxes[j] = __ldg(prop_boxes + gp);
   if (out_classes) out_classes[j] = prop_classes[gp];
+  if (out_field) out_field[j] = __ldg(prop_field + gp);  // pass-through proposal field (objectness_logits)
   const long long m = matches[gp];
   if (out_matched) out_matched[j] = m;
   if (out_gt_boxes) {
     const int g0 = gt_off[img], ng = gt_off[img + 1] - g0;
     out_gt_boxes[j] = ng > 0 ? __ldg(gt_boxes + g0 + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// add_ground_truth_to_proposals for a batch of images in ONE launch: image i's output rows are its proposals followed
+// by its ground-truth boxes (objectness logit of a GT box = gt_logit), images back to back -- the concatenated layout
+// the labelling kernels read, so the per-image results are views of one buffer and no further cat is needed.
+constexpr int APPEND_MAX_IMG = 32;
+struct AppendGtArgs {
+  const float4* prop[APPEND_MAX_IMG];
+  const float* logit[APPEND_MAX_IMG];
+  const float4* gt[APPEND_MAX_IMG];
+  int off[APPEND_MAX_IMG + 1];  // output row offsets of this launch's images
+  int np[APPEND_MAX_IMG];       // proposals per image
+  int n_img;
+  float gt_logit;
+};
+__global__ void append_gt_kernel(const AppendGtArgs a, float4* __restrict__ out_boxes, float* __restrict__ out_logits) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.off[a.n_img]) return;
+  int lo = 0, hi = a.n_img;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (a.off[mid] <= j) lo = mid; else hi = mid;
+  }
+  const int local = j - a.off[lo];
+  if (local < a.np[lo]) {
+    out_boxes[j] = __ldg(a.prop[lo] + local);
+    out_logits[j] = __ldg(a.logit[lo] + local);
+  } else {
+    out_boxes[j] = __ldg(a.gt[lo] + (local - a.np[lo]));
+    out_logits[j] = a.gt_logit;
   }
 }
 
@@ -301,8 +334,9 @@ int unit_sample_gather(const int64_t* pos_idx, const int64_t* neg_idx, const int
                        const int* gt_offsets, int n_img, int S_total, const float* prop_boxes,
                        const int64_t* prop_classes, const int64_t* matches, const float* gt_boxes,
                        int64_t* sampled_idx, float* out_boxes, int64_t* out_classes, int64_t* out_matched,
-                       float* out_gt_boxes, unit_stream_t stream) {
+                       float* out_gt_boxes, const float* prop_field, float* out_field, unit_stream_t stream) {
   UNIT_REQUIRE(n_img >= 0 && S_total >= 0, "sample_gather: bad shape");
+  UNIT_REQUIRE(!out_field || prop_field, "sample_gather: out_field without prop_field");
   if (S_total == 0 || n_img == 0) return UNIT_OK;
   UNIT_REQUIRE(pos_idx && neg_idx && perm_pos_offsets && perm_neg_offsets && pos_sel_offsets && neg_sel_offsets &&
                    prop_offsets && gt_offsets && prop_boxes && prop_classes && matches,
@@ -310,8 +344,46 @@ int unit_sample_gather(const int64_t* pos_idx, const int64_t* neg_idx, const int
   sample_gather_kernel<<<cdiv(S_total, 128), 128, 0, (cudaStream_t)stream>>>(
       pos_idx, neg_idx, perm_pos, perm_pos_offsets, perm_neg, perm_neg_offsets, pos_sel_offsets, neg_sel_offsets,
       prop_offsets, gt_offsets, n_img, S_total, (const float4*)prop_boxes, prop_classes, matches,
-      (const float4*)gt_boxes, sampled_idx, (float4*)out_boxes, out_classes, out_matched, (float4*)out_gt_boxes);
+      (const float4*)gt_boxes, sampled_idx, (float4*)out_boxes, out_classes, out_matched, (float4*)out_gt_boxes,
+      prop_field, out_field);
   UNIT_CHECK_LAUNCH("sample_gather_kernel");
+  return UNIT_OK;
+}
+
+int unit_append_gt(const float* const* prop_boxes, const float* const* prop_logits, const float* const* gt_boxes,
+                   const int* prop_counts, const int* gt_counts, int n_img, float gt_logit, float* out_boxes,
+                   float* out_logits, unit_stream_t stream) {
+  UNIT_REQUIRE(n_img >= 0, "append_gt: bad shape");
+  if (n_img == 0) return UNIT_OK;
+  UNIT_REQUIRE(prop_boxes && prop_logits && gt_boxes && prop_counts && gt_counts && out_boxes && out_logits,
+               "append_gt: null pointer");
+  UNIT_REQUIRE((((uintptr_t)out_boxes) & 15) == 0, "append_gt: out_boxes must be 16-byte aligned");
+  long long done = 0;
+  for (int i0 = 0; i0 < n_img; i0 += APPEND_MAX_IMG) {
+    AppendGtArgs a;
+    a.n_img = n_img - i0 < APPEND_MAX_IMG ? n_img - i0 : APPEND_MAX_IMG;
+    a.gt_logit = gt_logit;
+    a.off[0] = 0;
+    for (int k = 0; k < a.n_img; ++k) {
+      const int i = i0 + k;
+      UNIT_REQUIRE(prop_counts[i] >= 0 && gt_counts[i] >= 0, "append_gt: negative count");
+      UNIT_REQUIRE((prop_counts[i] == 0 || (prop_boxes[i] && prop_logits[i])) && (gt_counts[i] == 0 || gt_boxes[i]),
+                   "append_gt: null image pointer");
+      UNIT_REQUIRE((((uintptr_t)prop_boxes[i] | (uintptr_t)gt_boxes[i]) & 15) == 0,
+                   "append_gt: boxes must be 16-byte aligned");
+      a.prop[k] = (const float4*)prop_boxes[i];
+      a.logit[k] = prop_logits[i];
+      a.gt[k] = (const float4*)gt_boxes[i];
+      a.np[k] = prop_counts[i];
+      a.off[k + 1] = a.off[k] + prop_counts[i] + gt_counts[i];
+    }
+    const int rows = a.off[a.n_img];
+    if (rows > 0) {
+      append_gt_kernel<<<cdiv(rows, 256), 256, 0, (cudaStream_t)stream>>>(a, (float4*)out_boxes + done, out_logits + done);
+      UNIT_CHECK_LAUNCH("append_gt_kernel");
+    }
+    done += rows;
+  }
   return UNIT_OK;
 }
 

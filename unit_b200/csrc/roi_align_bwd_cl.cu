@@ -606,6 +606,7 @@ int launch_bwd_cl(const void* gout, const float* rois, void* gfeat, void* ws, in
   using namespace cl;
   const bool bf = dtype == UNIT_BF16;
   CUtensorMap map;
+  if (int rc = ensure_driver_context(gout)) return rc;
   {
     // fp32: rows = channels (196 floats, 784 B).  bf16: rows = channel PAIRS (2 x 196 bf16, 784 B).
     cuuint64_t dims[2] = {(cuuint64_t)(bf ? 2 * P * P : P * P), (cuuint64_t)R * C / (bf ? 2 : 1)};

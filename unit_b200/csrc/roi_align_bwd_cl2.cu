@@ -500,6 +500,7 @@ int launch_bwd_cl2(const void* gout, const float* rois, void* gfeat, void* ws, i
                    float scale, int sr, int aligned, cudaStream_t st) {
   using namespace cl2;
   CUtensorMap map;
+  if (int rc = ensure_driver_context(gout)) return rc;
   {
     cuuint64_t dims[2] = {(cuuint64_t)(P * P), (cuuint64_t)R * C};
     cuuint64_t strides[1] = {(cuuint64_t)(P * P) * sizeof(float)};

@@ -154,11 +154,32 @@ def subsample_labels(labels: torch.Tensor, num_samples: int, positive_fraction: 
     return positive[perm1], negative[perm2]
 
 
+def _plain_rpn_fields(p: Instances) -> bool:
+    """Proposals as the RPN emits them: fp32 CUDA proposal_boxes + objectness_logits and nothing else."""
+    f = p.get_fields()
+    if set(f) != {"proposal_boxes", "objectness_logits"}:
+        return False
+    b, l = f["proposal_boxes"].tensor, f["objectness_logits"]
+    return b.is_cuda and b.dtype == torch.float32 and l.dtype == torch.float32 and l.dim() == 1 and not ops._is_fake(b)
+
+
 def add_ground_truth_to_proposals(gt_boxes: List[Boxes], proposals: List[Instances]) -> List[Instances]:
     """[D2] proposal_utils.add_ground_truth_to_proposals: GT appended AFTER the RPN proposals."""
     assert len(proposals) == len(gt_boxes)
     out = []
     gt_logit_value = math.log((1.0 - 1e-10) / (1 - (1.0 - 1e-10)))
+    if proposals and all(_plain_rpn_fields(p) for p in proposals) and all(g.tensor.dtype == torch.float32 for g in gt_boxes):
+        # one launch for the whole batch; every image's fields are views of ONE buffer, so the labelling's cat is free
+        boxes, logits = ops.append_gt([p.proposal_boxes.tensor for p in proposals],
+                                      [p.objectness_logits for p in proposals], [g.tensor for g in gt_boxes],
+                                      gt_logit_value)
+        off = 0
+        for gt_i, prop_i in zip(gt_boxes, proposals):
+            n = len(prop_i) + len(gt_i)
+            out.append(Instances(prop_i.image_size, proposal_boxes=Boxes(boxes[off:off + n]),
+                                 objectness_logits=logits[off:off + n]))
+            off += n
+        return out
     for gt_i, prop_i in zip(gt_boxes, proposals):
         gt_prop = Instances(prop_i.image_size)
         gt_prop.proposal_boxes = gt_i
@@ -171,7 +192,7 @@ class LabelMatch:
     """Device-side result of the label phase (fused IoU+match, label+compaction) for a batch of images."""
 
     __slots__ = ("prop_counts", "gt_counts", "prop_boxes", "gt_boxes", "gt_classes", "po", "go", "matches", "mlabels",
-                 "vals", "prop_classes", "pos_idx", "neg_idx", "counts")
+                 "vals", "prop_classes", "pos_idx", "neg_idx", "counts", "prop_logits")
 
 
 def label_match(proposals: List[Instances], targets: List[Instances], *, num_classes: int,
@@ -182,6 +203,11 @@ def label_match(proposals: List[Instances], targets: List[Instances], *, num_cla
     lm.prop_counts = [len(p) for p in proposals]
     lm.gt_counts = [len(t) for t in targets]
     lm.prop_boxes = cat([p.proposal_boxes.tensor for p in proposals])
+    # the one pass-through field RPN proposals carry, concatenated like the boxes (a view when the images already share
+    # a buffer, as after add_ground_truth_to_proposals): gathered by the sampling launch itself
+    lm.prop_logits = (cat([p.objectness_logits for p in proposals])
+                      if all(p.has("objectness_logits") and p.objectness_logits.dtype == torch.float32
+                             and p.objectness_logits.dim() == 1 for p in proposals) else None)
     lm.gt_boxes = cat([t.gt_boxes.tensor for t in targets])
     lm.gt_classes = cat([t.gt_classes for t in targets]).to(torch.int64)
     lm.po = ops.offsets_from_counts(lm.prop_counts, dev)
@@ -256,15 +282,18 @@ def sample_from_draw(lm: LabelMatch, draw: SampleDraw, devbuf: torch.Tensor, pro
     d_perm_neg = devbuf[draw.pos_len:draw.pos_len + draw.neg_len]
     offs = devbuf[draw.pos_len + draw.neg_len:].view(torch.int32)
     k = n_img + 1
-    sampled, s_boxes, s_classes, s_matched, s_gt = ops.sample_gather(
+    res_g = ops.sample_gather(
         lm.pos_idx, lm.neg_idx, d_perm_pos, offs[:k], d_perm_neg, offs[k:2 * k], offs[2 * k:3 * k], offs[3 * k:4 * k],
-        lm.po, lm.go, S, lm.prop_boxes, lm.prop_classes, lm.matches, lm.gt_boxes)
+        lm.po, lm.go, S, lm.prop_boxes, lm.prop_classes, lm.matches, lm.gt_boxes, lm.prop_logits)
+    sampled, s_boxes, s_classes, s_matched, s_gt = res_g[:5]
+    s_logits = res_g[5] if lm.prop_logits is not None else None
     out, matched_list, vals_list = [], [], []
     off = 0
     num_fg, num_bg = [], []
     # pass-through proposal fields (objectness_logits ...): for more than two images ONE gather per field over the
     # concatenated field (global row = sampled row + the image's proposal offset) instead of one launch per image
-    extra = [n for n in proposals[0].get_fields() if n != "proposal_boxes"] if proposals else []
+    extra = [n for n in proposals[0].get_fields()
+             if n != "proposal_boxes" and not (n == "objectness_logits" and s_logits is not None)] if proposals else []
     batched = {}
     if n_img > 2 and extra:
         per_img = [(pso[i + 1] - pso[i]) + (nso[i + 1] - nso[i]) for i in range(n_img)]
@@ -291,7 +320,9 @@ def sample_from_draw(lm: LabelMatch, draw: SampleDraw, devbuf: torch.Tensor, pro
         res = Instances(p.image_size)
         res.proposal_boxes = Boxes(s_boxes[sl])
         for name, value in p.get_fields().items():
-            if name != "proposal_boxes":
+            if name == "objectness_logits" and s_logits is not None:
+                res.set(name, s_logits[sl])
+            elif name != "proposal_boxes":
                 res.set(name, batched[name][sl] if name in batched else value[idx])
         res.gt_classes = s_classes[sl]
         if lm.gt_counts[i] > 0:

@@ -283,8 +283,34 @@ def label_proposals(matches, mlabels, gt_classes, gt_offsets, prop_offsets, num_
     return prop_classes, pos_idx, neg_idx, counts
 
 
+def append_gt(prop_boxes: Sequence[torch.Tensor], prop_logits: Sequence[torch.Tensor],
+              gt_boxes: Sequence[torch.Tensor], gt_logit: float):
+    """[D2] add_ground_truth_to_proposals for all images in one launch: -> (boxes [T,4], logits [T]) with image i's
+    rows = its proposals followed by its GT boxes, images back to back (T = sum(P_i + G_i)).  fp32 CUDA inputs."""
+    dev = _need_cuda(*prop_boxes, *prop_logits, *gt_boxes)
+    n = len(prop_boxes)
+    pb = [_c(t, _F32) for t in prop_boxes]
+    pl = [_c(t, _F32) for t in prop_logits]
+    gb = [_c(t, _F32) for t in gt_boxes]
+    pc = [int(t.shape[0]) for t in pb]
+    gc = [int(t.shape[0]) for t in gb]
+    total = sum(pc) + sum(gc)
+    out_boxes = torch.empty((total, 4), dtype=_F32, device=dev)
+    out_logits = torch.empty((total,), dtype=_F32, device=dev)
+    if n and total:
+        vp = ctypes.c_void_p * n
+        ci = ctypes.c_int * n
+        check(lib().unit_append_gt(vp(*[t.data_ptr() for t in pb]), vp(*[t.data_ptr() for t in pl]),
+                                   vp(*[t.data_ptr() for t in gb]), ci(*pc), ci(*gc), n, float(gt_logit),
+                                   _ptr(out_boxes), _ptr(out_logits), _stream()), "unit_append_gt")
+    return out_boxes, out_logits
+
+
 def sample_gather(pos_idx, neg_idx, perm_pos, perm_pos_off, perm_neg, perm_neg_off, pos_sel_off, neg_sel_off,
-                  prop_offsets, gt_offsets, S_total: int, prop_boxes, prop_classes, matches, gt_boxes):
+                  prop_offsets, gt_offsets, S_total: int, prop_boxes, prop_classes, matches, gt_boxes,
+                  prop_field: Optional[torch.Tensor] = None):
+    """-> (sampled_idx, boxes, classes, matched, gt_boxes[, field]): ``prop_field`` is one fp32 pass-through field of
+    the proposals (objectness_logits), concatenated like prop_boxes and gathered by the same launch."""
     dev = _need_cuda(pos_idx)
     n_img = prop_offsets.numel() - 1
     sampled = torch.empty((S_total,), dtype=torch.int64, device=dev)
@@ -292,12 +318,19 @@ def sample_gather(pos_idx, neg_idx, perm_pos, perm_pos_off, perm_neg, perm_neg_o
     out_classes = torch.empty((S_total,), dtype=torch.int64, device=dev)
     out_matched = torch.empty((S_total,), dtype=torch.int64, device=dev)
     out_gt = torch.empty((S_total, 4), dtype=_F32, device=dev)
+    out_field = None
+    if prop_field is not None:
+        prop_field = _c(prop_field, _F32)
+        out_field = torch.empty((S_total,), dtype=_F32, device=dev)
     check(lib().unit_sample_gather(_ptr(pos_idx), _ptr(neg_idx), _ptr(perm_pos), _ptr(perm_pos_off), _ptr(perm_neg),
                                    _ptr(perm_neg_off), _ptr(pos_sel_off), _ptr(neg_sel_off), _ptr(prop_offsets),
                                    _ptr(gt_offsets), n_img, S_total, _ptr(_c(prop_boxes, _F32)), _ptr(prop_classes),
                                    _ptr(matches), _ptr(_c(gt_boxes, _F32)), _ptr(sampled), _ptr(out_boxes),
-                                   _ptr(out_classes), _ptr(out_matched), _ptr(out_gt), _stream()),
+                                   _ptr(out_classes), _ptr(out_matched), _ptr(out_gt), _ptr(prop_field),
+                                   _ptr(out_field), _stream()),
           "unit_sample_gather")
+    if prop_field is not None:
+        return sampled, out_boxes, out_classes, out_matched, out_gt, out_field
     return sampled, out_boxes, out_classes, out_matched, out_gt
 
 
@@ -960,6 +993,7 @@ class _FTStepLossFn(torch.autograd.Function):
         ctx.K1 = K1
         ctx.n_cols = 5 * spec.K + 1
         total = losses[2]
+        ctx.set_materialize_grads(False)  # no zero tensors for the unused gradients of scores / bbox / total
         ctx.mark_non_differentiable(scores, bbox, total)
         return losses[0], losses[1], scores, bbox, total
 
@@ -977,7 +1011,12 @@ class _FTStepLossFn(torch.autograd.Function):
         else:
             dst = [torch.empty_like(p) if n else None for p, n in zip(params, need)]
             ret = tuple(dst)
-        sc = [_c(g_cls.reshape(1), _F32), _c(g_box.reshape(1), _F32)]
+        if g_cls is None and g_box is None:
+            return (None,) * 13
+        zero = None
+        if g_cls is None or g_box is None:  # only one of the two losses was differentiated
+            zero = torch.zeros((1,), dtype=_F32, device=x.device)
+        sc = [zero if g is None else _c(g.reshape(1), _F32) for g in (g_cls, g_box)]
         # overwrite_bound_grads(): the caller guarantees the bound buffers hold nothing to keep (it would have zeroed
         # them), so the kernel writes instead of accumulating and the zero fill is not needed
         predictor_wgrad(d_packed, x, ctx.n_cols, [0, ctx.K1, ctx.n_cols], [dst[0], dst[2]], [dst[1], dst[3]], sc,
