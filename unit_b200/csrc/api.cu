@@ -67,7 +67,6 @@ const Switches& switches() {
     Switches v;
     v.filter_single = getenv("UNIT_FILTER_SINGLE") != nullptr;
     v.nms_single = getenv("UNIT_NMS_SINGLE") != nullptr;
-    v.fwd_band_bf16 = getenv("UNIT_ROI_FWD_BAND_BF16") != nullptr;
     v.fwd_v3 = getenv("UNIT_ROI_FWD_V3") != nullptr;
     v.bwd_v4 = getenv("UNIT_ROI_BWD_V4") != nullptr;
     v.bwd_cl1 = getenv("UNIT_ROI_BWD_CL1") != nullptr;

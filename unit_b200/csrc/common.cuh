@@ -51,7 +51,7 @@ int ensure_driver_context(const void* dev_ptr);
 
 // Developer switches (kernel-variant experiments), read from the environment ONCE per process -- never on a launch path.
 struct Switches {
-  bool filter_single, nms_single, fwd_band_bf16, fwd_v3, bwd_v4, bwd_cl1, paste_flat;
+  bool filter_single, nms_single, fwd_v3, bwd_v4, bwd_cl1, paste_flat;
   int roi_debug, bwd_promo, bwd_evict_first, bwd2_evict_first, bwd_sweep3;
 };
 const Switches& switches();

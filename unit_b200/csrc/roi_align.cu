@@ -125,7 +125,7 @@ int launch_fwd_slab2(const void* feat, const float* rois, void* out, int N, int 
 bool fwd_band_fits(int C, int H, int W, int dtype);
 size_t fwd_band_workspace_bytes(int R);
 int launch_fwd_band(const void* feat, const float* rois, void* out, void* tabs_ws, int N, int C, int H, int W, int R,
-                    float scale, int sr, int aligned, int dtype, const int* img_off, cudaStream_t st);
+                    float scale, int sr, int aligned, int dtype, int* img_off, cudaStream_t st);
 bool bwd_slab2_fits(int C, int H, int W, int dtype);
 size_t bwd_slab2_workspace_bytes(int N, int C, int H, int W, int dtype);
 int launch_bwd_slab2(const void* gout, const float* rois, void* gfeat, void* f32_scratch, int N, int C, int H, int W,
@@ -171,10 +171,9 @@ int unit_roi_align_fwd(const void* feat, const float* rois, void* out, int N, in
       return UNIT_EWORKSPACE;
     }
     UNIT_REQUIRE((((uintptr_t)out) & 15) == 0, "roi_align_fwd: out must be 16-byte aligned");
-    roi_offsets_kernel<<<cdiv(R + 1, 256), 256, 0, st>>>(rois, R, N, (int*)workspace);
-    UNIT_CHECK_LAUNCH("roi_offsets_kernel");
+    // the per-image offsets are written by the table kernel (first words of the workspace)
     return launch_fwd_band(feat, rois, out, (char*)workspace + offsets_bytes(N), N, C, H, W, R, spatial_scale,
-                           sampling_ratio, aligned, dtype, (const int*)workspace, st);
+                           sampling_ratio, aligned, dtype, (int*)workspace, st);
   }
   if (rois_sorted && PH == 14 && PW == 14 && N > 0 && fwd_slab2_fits(C, H, W, dtype)) {
     if (!workspace || workspace_bytes < offsets_bytes(N)) {

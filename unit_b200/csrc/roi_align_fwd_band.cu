@@ -117,13 +117,22 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t
 // one warp per RoI
 __global__ void __launch_bounds__(128)
 roi_tables_kernel(const float* __restrict__ rois, RoiTab* __restrict__ tabs, int R, int N, int H, int W, float scale,
-                  int sampling_ratio, int aligned) {
+                  int sampling_ratio, int aligned, int* __restrict__ img_off) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= R) return;
   const float* roi = rois + (long long)r * 5;
   RoiTab* t = tabs + r;
   const int n = (int)roi[0];
+  if (lane == 0) {
+    // per-image RoI offsets from the (sorted) batch-index column, img_off[k] = first RoI of image >= k: the RoI where
+    // the index steps writes the entries it passes, the last RoI also the tail (was a launch of its own)
+    const int cur = min(max(n, 0), N);
+    const int prev = r > 0 ? min(max((int)roi[-5], 0), N) : -1;
+    for (int k = prev + 1; k <= cur; ++k) img_off[k] = r;
+    if (r == R - 1)
+      for (int k = cur + 1; k <= N; ++k) img_off[k] = R;
+  }
   const Geom g = roi_geom(roi, scale, P, P, sampling_ratio, aligned);
   int mode = 1;
   if (g.gw <= 0 || g.gh <= 0 || n < 0 || n >= N) mode = 0;
@@ -550,9 +559,9 @@ size_t fwd_band_workspace_bytes(int R) { return (size_t)(R > 0 ? R : 1) * sizeof
 
 template <typename T>
 static int launch_band_t(const void* feat, const float* rois, void* out, void* tabs_ws, int N, int C, int H, int W,
-                         int R, float scale, int sr, int aligned, const int* img_off, cudaStream_t st) {
+                         int R, float scale, int sr, int aligned, int* img_off, cudaStream_t st) {
   band::RoiTab* tabs = reinterpret_cast<band::RoiTab*>(tabs_ws);
-  band::roi_tables_kernel<<<cdiv(R, 4), 128, 0, st>>>(rois, tabs, R, N, H, W, scale, sr, aligned);
+  band::roi_tables_kernel<<<cdiv(R, 4), 128, 0, st>>>(rois, tabs, R, N, H, W, scale, sr, aligned, img_off);
   UNIT_CHECK_LAUNCH("roi_tables_kernel");
   v2::Params p;
   p.feat = feat;
@@ -581,7 +590,7 @@ static int launch_band_t(const void* feat, const float* rois, void* out, void* t
 }
 
 int launch_fwd_band(const void* feat, const float* rois, void* out, void* tabs_ws, int N, int C, int H, int W, int R,
-                    float scale, int sr, int aligned, int dtype, const int* img_off, cudaStream_t st) {
+                    float scale, int sr, int aligned, int dtype, int* img_off, cudaStream_t st) {
   if (dtype == UNIT_F32)
     return launch_band_t<float>(feat, rois, out, tabs_ws, N, C, H, W, R, scale, sr, aligned, img_off, st);
   return launch_band_t<__nv_bfloat16>(feat, rois, out, tabs_ws, N, C, H, W, R, scale, sr, aligned, img_off, st);
