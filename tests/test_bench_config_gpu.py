@@ -12,6 +12,7 @@ it against the CPU oracle (torchvision CPU ROIAlign + restated Detectron2 / UniT
 """
 import pytest
 import torch
+import torchvision  # noqa: F401  (registers torch.ops.torchvision.*: the CPU reference kernels used below)
 
 from conftest import assert_close_rms, random_boxes, seeded
 

@@ -4,6 +4,7 @@ import os
 
 import pytest
 import torch
+import torchvision  # noqa: F401  (registers torch.ops.torchvision.*)
 from torch import nn
 
 from conftest import ROOT, assert_close_rms, load_golden, random_boxes, seeded

@@ -90,6 +90,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   unsigned char* sa = base;
   unsigned char* sb = base + NSTAGE * a_bytes;
   __shared__ __align__(8) uint64_t full_bar[NSTAGE];
+  __shared__ __align__(8) uint64_t empty_bar[NSTAGE];
   __shared__ __align__(8) uint64_t done_bar;
   __shared__ uint32_t tmem_base_smem;
 
@@ -105,7 +106,10 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (nkb < 0) nkb = 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
     mbar_init(&done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -120,24 +124,27 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t tmem = tmem_base_smem;
 
   if (warp == 0 && lane == 0) {
-    // ---- TMA producer: every k-block of this split is in flight at once (nkb <= NSTAGE)
-    for (int s = 0; s < nkb; ++s) {
+    // ---- TMA producer: a ring of NSTAGE stages; a stage is refilled when the MMAs that read it have completed
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % NSTAGE;
+      if (kb >= NSTAGE) mbar_wait(&empty_bar[s], (uint32_t)((kb / NSTAGE) - 1) & 1u);
       mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + b_bytes));
-      tma_load_2d(sa + s * a_bytes, ma, &full_bar[s], (kb0 + s) * BK, m0);
-      tma_load_2d(sb + s * b_bytes, mb, &full_bar[s], (kb0 + s) * BK, n_tile * NP);
+      tma_load_2d(sa + s * a_bytes, ma, &full_bar[s], (kb0 + kb) * BK, m0);
+      tma_load_2d(sb + s * b_bytes, mb, &full_bar[s], (kb0 + kb) * BK, n_tile * NP);
     }
   } else if (warp == 1 && lane == 0) {
     // ---- MMA issuer
     // instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 << 7, 2 << 10), K-major both, N >> 3 at 17, M >> 4 at 24
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    for (int s = 0; s < nkb; ++s) {
-      mbar_wait(&full_bar[s], 0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % NSTAGE;
+      mbar_wait(&full_bar[s], (uint32_t)(kb / NSTAGE) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_addr = smem_u32(sa + s * a_bytes), b_addr = smem_u32(sb + s * b_bytes);
 #pragma unroll
       for (int k = 0; k < BK / UK; ++k) {
         const uint64_t da = make_desc(a_addr + k * UK * 4), db = make_desc(b_addr + k * UK * 4);
-        const uint32_t accumulate = (s > 0 || k > 0) ? 1u : 0u;
+        const uint32_t accumulate = (kb > 0 || k > 0) ? 1u : 0u;
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
@@ -147,6 +154,10 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
             : "memory");
       }
+      if (kb + NSTAGE < nkb)  // the stage is used again: hand it back when the MMAs above have read it
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(&empty_bar[s]))
+                     : "memory");
     }
     // arrives on done_bar when every MMA above has completed (implies tcgen05.fence::before_thread_sync)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&done_bar))
@@ -208,7 +219,19 @@ __global__ void splitk_reduce_kernel(const ReduceArgs a0, const ReduceArgs a1, i
   float acc = 0.f;
   if (n < a.N) {
     acc = a.bias ? a.bias[n] : 0.f;
-    for (int s = 0; s < splits; ++s) acc += a.partial[((size_t)s * MP + m) * a.ldp + n];
+    // eight loads in flight, summed in split order (a plain loop over a run-time count issues them one by one: the
+    // kernel was a chain of `splits` L2 round trips)
+    const float* src = a.partial + (size_t)m * a.ldp + n;
+    const size_t step = (size_t)MP * a.ldp;
+    int s = 0;
+    for (; s + 8 <= splits; s += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (size_t)(s + j) * step);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += v[j];
+    }
+    for (; s < splits; ++s) acc += __ldg(src + (size_t)s * step);
   }
   a.out[(size_t)m * a.ldy + n] = acc;
 }
@@ -252,7 +275,20 @@ static void plan(int M, int N, int K, Params* p) {
   const int per = (N + p->n_tiles - 1) / p->n_tiles;
   p->NP = ((per + 15) / 16) * 16;
   const int kb_total = (K + BK - 1) / BK;
-  p->splits = (kb_total + NSTAGE - 1) / NSTAGE;
+  p->splits = (kb_total + NSTAGE - 1) / NSTAGE;  // upper bound (sizes the workspace); choose_splits() lowers it
+}
+
+// K splits so that the whole grid is ONE wave (one CTA per SM: the operand ring takes most of the shared memory): with
+// a split per NSTAGE k-blocks a [1024 x 288 x 2048] grouped problem was 384 CTAs = 2.6 waves, each paying the
+// prologue (barriers, TMEM allocation) and the epilogue (its partial tile), and 16 partials to reduce; 6 splits of 11
+// k-blocks through the ring are 144 CTAs and 6 partials.
+static int choose_splits(int K, int tiles, int upper) {
+  const int kb_total = (K + BK - 1) / BK;
+  int target = sm_count() / (tiles > 0 ? tiles : 1);
+  if (target < 1) target = 1;
+  if (target > upper) target = upper;
+  const int kb_per = (kb_total + target - 1) / target;
+  return (kb_total + kb_per - 1) / kb_per;
 }
 
 
@@ -421,7 +457,19 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, const flo
     float* dst = sg.w_dst[s];
     if (!dst) return;
     float acc = 0.f;
-    for (int sp = 0; sp < splits; ++sp) acc += partial[((size_t)sp * BM + n) * K + k];
+    {
+      const float* src = partial + (size_t)n * K + k;
+      const size_t step = (size_t)BM * K;
+      int sp = 0;
+      for (; sp + 8 <= splits; sp += 8) {  // eight loads in flight, summed in split order
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (size_t)(sp + j) * step);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += v[j];
+      }
+      for (; sp < splits; ++sp) acc += __ldg(src + (size_t)sp * step);
+    }
     if (sg.scale[s]) acc *= *sg.scale[s];
     float* o = dst + (size_t)(n - sg.row0[s]) * K + k;
     *o = accumulate ? *o + acc : acc;
@@ -437,7 +485,17 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, const flo
   float* dst = sg.b_dst[s];
   if (!dst) return;
   float acc = 0.f;
-  for (int r = lane; r < R; r += 32) acc += gy[(size_t)r * ldg + n];
+  {
+    int r = lane;
+    for (; r + 7 * 32 < R; r += 8 * 32) {  // eight loads in flight per lane (was one L2 round trip per row)
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldg(gy + (size_t)(r + 32 * j) * ldg + n);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += v[j];
+    }
+    for (; r < R; r += 32) acc += __ldg(gy + (size_t)r * ldg + n);
+  }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) {
     if (sg.scale[s]) acc *= *sg.scale[s];
@@ -527,6 +585,7 @@ int unit_predictor_gemm2(const float* x1, const float* w1, const float* b1, floa
     if (rc) return rc;
     if (q.NP > np_max) np_max = q.NP;
   }
+  p.splits = choose_splits(K, (mp / BM) * (p.n_tiles + p.n_tiles2), p.splits);
   const size_t smem = (size_t)NSTAGE * (BM * BK * 4 + np_max * BK * 4) + 1024;
   UNIT_CUDA(cudaFuncSetAttribute(tf32_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(mp / BM, p.n_tiles + p.n_tiles2, p.splits);

@@ -583,11 +583,7 @@ static EncodeTiledFn encode_fn() {
 
 }  // namespace cl
 
-// epilogue kernels shared with roi_align_bwd_cl2.cu
-void launch_bwd_cl_zero(void* ws, long long n4, cudaStream_t st) {
-  const int zgrid = (int)std::min<long long>((n4 + 255) / 256, (long long)sm_count() * 8);
-  cl::zero4_kernel<<<zgrid, 256, 0, st>>>((float4*)ws, n4);
-}
+// epilogue kernel shared with roi_align_bwd_cl2.cu
 void launch_bwd_cl_unpermute(const float* scratch, void* gfeat, int N, int C, int HW, bool bf16, cudaStream_t st) {
   dim3 tgrid((HW + 31) / 32, C / cl::CB, N);
   if (bf16) cl::unpermute_kernel<true><<<tgrid, 256, 0, st>>>(scratch, gfeat, C, HW);

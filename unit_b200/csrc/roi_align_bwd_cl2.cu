@@ -168,9 +168,18 @@ __device__ __forceinline__ bool build_axis(float start, float bin, int g, int si
   return jump;
 }
 
+// One launch prepares the main kernel's inputs: blocks [0, tab_blocks) build the RoI tables (one warp per RoI), the
+// others clear the workspace head (work counter + channel-last image) -- two kernels before, back to back on the
+// critical path of the step.
 __global__ void __launch_bounds__(128)
-bwd_tables_kernel(const float* __restrict__ rois, RoiTab* __restrict__ tabs, int R, int N, int H, int W, float scale,
-                  int sampling_ratio, int aligned) {
+bwd_prepare_kernel(const float* __restrict__ rois, RoiTab* __restrict__ tabs, int R, int N, int H, int W, float scale,
+                   int sampling_ratio, int aligned, int tab_blocks, float4* __restrict__ zero, long long n4) {
+  if ((int)blockIdx.x >= tab_blocks) {
+    const long long stride = (long long)(gridDim.x - tab_blocks) * blockDim.x;
+    for (long long i = (long long)(blockIdx.x - tab_blocks) * blockDim.x + threadIdx.x; i < n4; i += stride)
+      zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= R) return;
@@ -492,7 +501,6 @@ static EncodeTiledFn encode_fn() {
 size_t bwd_cl2_table_bytes(int R) { return (size_t)(R > 0 ? R : 1) * sizeof(cl2::RoiTab) + 256; }
 
 // kernels of roi_align_bwd_cl.cu reused for the epilogue
-void launch_bwd_cl_zero(void* ws, long long n4, cudaStream_t st);
 void launch_bwd_cl_unpermute(const float* scratch, void* gfeat, int N, int C, int HW, bool bf16, cudaStream_t st);
 
 // workspace: [256 B counter][N*H*W*C fp32 channel-last image (+64 B)][R tables]
@@ -535,10 +543,14 @@ int launch_bwd_cl2(const void* gout, const float* rois, void* gfeat, void* ws, i
   // tiles: evict_normal, so the 64-byte DRAM granules two neighbouring tiles share are fetched once (with the image
   // pinned by the reductions' evict_last hint): DRAM read 1.17 GB -> 0.94 GB, same time (profiles/r02_roi_align_bwd.md)
   p.evict_first = switches().bwd2_evict_first;
-  bwd_tables_kernel<<<cdiv(R, 4), 128, 0, st>>>(rois, tabs, R, N, H, W, scale, sr, aligned);
-  UNIT_CHECK_LAUNCH("bwd_tables_kernel");
-  launch_bwd_cl_zero(ws, total / 4 + 16, st);
-  UNIT_CHECK_LAUNCH("zero4_kernel");
+  {
+    const int tab_blocks = cdiv(R, 4);
+    const long long n4 = total / 4 + 16;
+    const int zero_blocks = (int)std::min<long long>((n4 + 127) / 128, (long long)sm_count() * 16);
+    bwd_prepare_kernel<<<tab_blocks + zero_blocks, 128, 0, st>>>(rois, tabs, R, N, H, W, scale, sr, aligned, tab_blocks,
+                                                                  (float4*)ws, n4);
+    UNIT_CHECK_LAUNCH("bwd_prepare_kernel");
+  }
   const size_t smem = (size_t)NW * sizeof(WarpArea);
   const long long items = (long long)R * (C / CB);
   long long grid = (items + NW - 1) / NW;
