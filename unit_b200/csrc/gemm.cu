@@ -23,7 +23,10 @@ namespace gemm {
 constexpr int BM = 128;        // rows per CTA (UMMA M)
 constexpr int BK = 32;         // fp32 elements per 128-byte swizzle row
 constexpr int UK = 8;          // K per tcgen05.mma kind::tf32
-constexpr int NSTAGE = 4;      // k-blocks per CTA, all in flight at once
+#ifndef UNIT_GEMM_NSTAGE
+#define UNIT_GEMM_NSTAGE 4
+#endif
+constexpr int NSTAGE = UNIT_GEMM_NSTAGE;  // operand ring depth (k-blocks in flight per CTA)
 constexpr int MAXN = 256;      // UMMA N limit
 
 struct Params {
@@ -302,7 +305,10 @@ static int choose_splits(int K, int tiles, int upper) {
 // wgrad_reduce_kernel, which also scales the rows (dL/dloss), adds the bias column sums and writes -- or accumulates
 // -- straight into the parameter-gradient buffers (the flat NCCL bucket).
 constexpr int WG_KR = 32;      // RoI rows per stage
-constexpr int WG_NT = 256;     // feature columns per CTA (UMMA N)
+#ifndef UNIT_WGRAD_NT
+#define UNIT_WGRAD_NT 128
+#endif
+constexpr int WG_NT = UNIT_WGRAD_NT;  // feature columns per CTA (UMMA N)
 constexpr int WG_STAGES = 4;   // stages per CTA, all in flight: 128 RoIs per CTA
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
