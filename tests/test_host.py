@@ -89,6 +89,43 @@ def test_heads_build_with_reference_state_dict_keys():
     assert head.box_pooler.aligned and head.box_pooler.output_size == (14, 14) and head.box_pooler.scales == (1 / 16,)
 
 
+def test_stage_skips_the_bucket_zero_only_when_it_owns_exactly_the_ft_gradients():
+    """RoIStage lets the weight-gradient kernel OVERWRITE the flat bucket (no zero fill, no loss add) only when the
+    bucket holds exactly cls_score_ft / bbox_pred_ft -- the four tensors the fused node writes; host logic only."""
+    import torch
+
+    from unit_b200 import ops
+    from unit_b200.config import load_cfg
+    from unit_b200.distributed import FlatGradBucket
+    from unit_b200.predictors import LossDict
+    from unit_b200.roi_heads import build_roi_heads
+    from unit_b200.stage import RoIStage
+    from unit_b200.structures import ShapeSpec
+
+    cfg = load_cfg(os.path.join(ROOT, "configs", "voc_split1_ft.yaml"),
+                   ["MODEL.ROI_HEADS.EMBEDDING_PATH", os.path.join(ROOT, "tests", "golden", "glove_mean.pt")])
+    head = build_roi_heads(cfg, {"res4": ShapeSpec(channels=1024, stride=16)})
+    ft = [p for p in head.parameters() if p.requires_grad]
+    assert len(ft) == 4
+    stage = RoIStage(head, lambda pooled: (pooled, pooled), FlatGradBucket(ft))
+    assert stage._bucket_is_exactly(head.box_predictor)
+    extra = torch.nn.Parameter(torch.zeros(3))
+    stage.bucket = FlatGradBucket(ft + [extra])
+    assert not stage._bucket_is_exactly(head.box_predictor)  # something else lives in the bucket: zero + accumulate
+    stage.bucket = None
+    assert not stage._bucket_is_exactly(head.box_predictor)
+    # the context only affects the backward that runs inside it
+    assert ops._OVERWRITE_BOUND[0] is False
+    with ops.overwrite_bound_grads():
+        assert ops._OVERWRITE_BOUND[0] is True
+    assert ops._OVERWRITE_BOUND[0] is False
+    # the losses dict the trainer sums is unchanged by the extra attribute
+    d = LossDict(loss_cls=torch.tensor(1.0), loss_box_reg=torch.tensor(2.0))
+    d.total = torch.tensor(3.0)
+    assert sorted(d) == ["loss_box_reg", "loss_cls"] and float(sum(d.values())) == 3.0
+    assert getattr({"loss_cls": 1}, "total", None) is None
+
+
 def test_containers():
     from unit_b200.structures import Boxes, Instances
 
