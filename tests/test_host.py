@@ -109,6 +109,9 @@ def test_stage_skips_the_bucket_zero_only_when_it_owns_exactly_the_ft_gradients(
     assert len(ft) == 4
     stage = RoIStage(head, lambda pooled: (pooled, pooled), FlatGradBucket(ft))
     assert stage._bucket_is_exactly(head.box_predictor)
+    ft[0].requires_grad_(False)  # frozen after the bucket was built: its slice would never be written
+    assert not stage._bucket_is_exactly(head.box_predictor)
+    ft[0].requires_grad_(True)
     extra = torch.nn.Parameter(torch.zeros(3))
     stage.bucket = FlatGradBucket(ft + [extra])
     assert not stage._bucket_is_exactly(head.box_predictor)  # something else lives in the bucket: zero + accumulate

@@ -161,7 +161,9 @@ class RoIStage:
         if any(m is None for m in want):
             return False
         ids = {id(m.weight) for m in want} | {id(m.bias) for m in want}
-        return {id(p) for p in self.bucket.params} == ids
+        # every one of them must still be trainable: a tensor frozen after the bucket was built gets no gradient
+        # written, and without the zero fill its slice would be all-reduced as it was left
+        return {id(p) for p in self.bucket.params} == ids and all(p.requires_grad for p in self.bucket.params)
 
     def _roi_backward(self, features, rois, pooled, grad_pooled_fn):
         if grad_pooled_fn is None:
